@@ -1,0 +1,122 @@
+/*
+ * rfv.h -- C ABI of the B200 (sm_100a) rectified-flow Euler-integration engine.
+ *
+ * The reference (AlbertGoTri/rectified-flow-vision) has no FFI / plugin interface: its boundary for this path is
+ * the Python API re-exported by models/__init__.py:5-12.  This header is the C-ABI seam UNDER that API: every
+ * entry point below replaces the numerical body of one reference function, takes plain pointers and sizes
+ * (no torch types), never throws, and returns 0 on success or a negative rfv_status with a message retrievable
+ * from rfv_last_error().  One handle per GPU; a handle is not thread-safe.  All device pointers are on the
+ * handle's device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * Layout contract at the boundary (what the reference's callers hold): contiguous NCHW fp32 images,
+ * fp32 time vector t[B], fp32 OIHW parameters named exactly like the reference state_dict
+ * ("velocity_net.enc_blocks.0.conv1.weight", ... 174 tensors, models/unet.py:157-227).
+ * Inside the engine activations are NHWC bf16, accumulators / GroupNorm statistics / Euler state are fp32.
+ */
+#ifndef RFV_H_
+#define RFV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFV_ABI_VERSION 1
+#define RFV_MAX_LEVELS 8
+
+typedef struct rfv_engine* rfv_handle;
+
+typedef enum {
+    RFV_OK = 0,
+    RFV_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    RFV_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+    RFV_ERR_STATE = -3,     /* weights not (fully) loaded, batch larger than capacity, ... */
+    RFV_ERR_NOMEM = -4
+} rfv_status;
+
+/* Mirrors the constructor arguments of UNet / BaseFlowModel (models/unet.py:136-145, models/base_flow.py:37-47).
+ * attention_resolutions and dropout are not here: the former is ignored by the reference (models/unet.py:143),
+ * the latter is identity on the eval-mode path this engine implements. */
+typedef struct {
+    int32_t image_size;                     /* S: images are [C, S, S] */
+    int32_t in_channels;                    /* 3 */
+    int32_t out_channels;                   /* = in_channels for flow models (models/base_flow.py:58) */
+    int32_t model_channels;                 /* 64; must be a multiple of 64 */
+    int32_t num_levels;                     /* len(channel_mult) */
+    int32_t channel_mult[RFV_MAX_LEVELS];   /* [1,2,4] */
+    int32_t num_res_blocks;                 /* 2 */
+    int32_t num_heads;                      /* 4 (models/unet.py:70) */
+    int32_t micro_batch;                    /* images integrated together; activation arena capacity */
+    int32_t device;                         /* CUDA ordinal */
+    int32_t flags;                          /* RFV_FLAG_* */
+} rfv_config;
+
+#define RFV_FLAG_NO_UMMA   1   /* force the mma.sync implicit-GEMM kernel everywhere (debug / A-B testing) */
+#define RFV_FLAG_NO_GRAPH  2   /* launch kernels directly instead of replaying a captured CUDA graph */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int rfv_abi_version(void);
+const char* rfv_last_error(void);
+int rfv_create(const rfv_config* cfg, rfv_handle* out);
+int rfv_destroy(rfv_handle h);
+
+/* ---- parameters: replaces nn.Module.load_state_dict / state_dict for the engine's packed copies
+ *      (BaseFlowModel.load/save, models/base_flow.py:210-226 stay in Python and keep the .pt format) ------- */
+int rfv_num_tensors(rfv_handle h);
+/* name and element count of the i-th parameter tensor the engine expects (reference state_dict names). */
+int rfv_tensor_info(rfv_handle h, int index, char* name_buf, int name_buf_len, int64_t* numel);
+/* Upload one fp32 tensor (DEVICE pointer, reference layout: conv OIHW, linear [out,in], vectors [C]);
+ * the engine repacks it (bf16 K-major [O][kh][kw][I] for tensor-core convs). */
+int rfv_set_tensor(rfv_handle h, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+/* Read a packed tensor back as fp32 in reference layout (bf16-rounded where the engine stores bf16). */
+int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+/* v = velocity_net(x, t): UNet.forward, models/unet.py:229-275 via BaseFlowModel.forward, models/base_flow.py:91-102.
+ * x, v: [B,C,S,S] fp32 NCHW device; t: [B] fp32 device.  Any B >= 1 (processed in micro-batches). */
+int rfv_velocity(rfv_handle h, const float* x, const float* t, float* v, int64_t batch, void* stream);
+
+/* In-place N-step explicit Euler: for i < num_steps: x += dt * v(x, i*dt), dt = 1/num_steps
+ * (BaseFlowModel.sample loop, models/base_flow.py:158-173; sample_with_trajectory :196-208).
+ * x: [B,C,S,S] fp32 NCHW device, updated in place (the Python wrapper clones the caller's noise first).
+ * traj (optional, may be NULL): [num_steps/save_every, B, C, S, S] fp32 device, receives x after every
+ * save_every-th step. */
+int rfv_euler_sample(rfv_handle h, float* x, int64_t batch, int num_steps, float* traj, int save_every,
+                     void* stream);
+
+/* Same integration with HOST buffers (pinned or pageable): noise_host -> out_host, [N,C,S,S] fp32.
+ * Host<->device copies are pipelined with compute on internal streams; this is the call behind
+ * generate_reflow_pairs (models/rectified_flow.py:127-174) and the bench's end-to-end number.
+ * out_host may alias noise_host. */
+int rfv_euler_sample_host(rfv_handle h, const float* noise_host, float* out_host, int64_t n, int num_steps);
+
+/* Euler loop that also accumulates mean((v - (x1-x0))^2) per step:
+ * RectifiedFlowModel.compute_straightness, models/rectified_flow.py:98-124.  x0, x1 device fp32 NCHW;
+ * dev_out: [num_points] fp32 DEVICE (per-step MSE; the caller averages).  No per-step host sync. */
+int rfv_straightness(rfv_handle h, const float* x0, const float* x1, int64_t batch, int num_points,
+                     float* dev_out, void* stream);
+
+/* Flow-matching forward loss: x_t = (1-t) x0 + t x1, target = x1 - x0 (BaseFlowModel.get_interpolation,
+ * models/base_flow.py:81-89), loss = mean((v(x_t,t) - target)^2) (models/rectified_flow.py:222-231), eval-mode
+ * network.  loss_out: 1 fp32 DEVICE value. */
+int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch,
+                float* loss_out, void* stream);
+
+/* ---- introspection for tests / bench -------------------------------------------------------------------- */
+/* Number of engine kernels launched (or graph-replayed) since the last call with reset != 0. */
+int64_t rfv_launch_count(rfv_handle h, int reset);
+/* Algorithmic FLOPs of one velocity evaluation per image (2*MAC convs/linears + 4*C*N^2 attention). */
+double rfv_flops_per_image(rfv_handle h);
+/* Copy a named intermediate activation of the LAST micro-batch of the last rfv_velocity call, converted to fp32
+ * NCHW (names: "input_conv", "enc_blocks.0", "downsamples.0", "mid_block1", "mid_attn", "dec_blocks.3",
+ * "upsamples.1", ...).  Returns the element count, or a negative status.  Test hook. */
+int64_t rfv_debug_activation(rfv_handle h, const char* name, float* dev_out, int64_t capacity, void* stream);
+/* Event-timed duration (ms) of each kernel class inside the last call made with profiling enabled. */
+int rfv_set_profiling(rfv_handle h, int enabled);
+int rfv_profile_report(rfv_handle h, char* buf, int buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFV_H_ */

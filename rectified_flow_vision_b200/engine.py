@@ -1,0 +1,257 @@
+"""ctypes binding of include/rfv.h: the only door from Python into the CUDA path.
+
+No torch types cross the boundary: tensors are passed as raw device pointers (``Tensor.data_ptr()``) plus
+sizes, the stream as ``torch.cuda.current_stream().cuda_stream``.  If the shared library cannot be loaded the
+import of this module still succeeds (so the parameter container / checkpoint I/O work on a CPU box) but any
+attempt to compute raises -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+from . import _build
+
+RFV_MAX_LEVELS = 8
+FLAG_NO_UMMA = 1
+FLAG_NO_GRAPH = 2
+
+
+class RfvConfig(C.Structure):
+    _fields_ = [("image_size", C.c_int32), ("in_channels", C.c_int32), ("out_channels", C.c_int32),
+                ("model_channels", C.c_int32), ("num_levels", C.c_int32),
+                ("channel_mult", C.c_int32 * RFV_MAX_LEVELS), ("num_res_blocks", C.c_int32),
+                ("num_heads", C.c_int32), ("micro_batch", C.c_int32), ("device", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+# every symbol include/rfv.h declares: (restype, argtypes)
+_VP, _FP, _I64 = C.c_void_p, C.c_void_p, C.c_int64
+SYMBOLS = {
+    "rfv_abi_version": (C.c_int, []),
+    "rfv_last_error": (C.c_char_p, []),
+    "rfv_create": (C.c_int, [C.POINTER(RfvConfig), C.POINTER(_VP)]),
+    "rfv_destroy": (C.c_int, [_VP]),
+    "rfv_num_tensors": (C.c_int, [_VP]),
+    "rfv_tensor_info": (C.c_int, [_VP, C.c_int, C.c_char_p, C.c_int, C.POINTER(_I64)]),
+    "rfv_set_tensor": (C.c_int, [_VP, C.c_char_p, _FP, _I64, _VP]),
+    "rfv_get_tensor": (C.c_int, [_VP, C.c_char_p, _FP, _I64, _VP]),
+    "rfv_velocity": (C.c_int, [_VP, _FP, _FP, _FP, _I64, _VP]),
+    "rfv_euler_sample": (C.c_int, [_VP, _FP, _I64, C.c_int, _FP, C.c_int, _VP]),
+    "rfv_euler_sample_host": (C.c_int, [_VP, _FP, _FP, _I64, C.c_int]),
+    "rfv_straightness": (C.c_int, [_VP, _FP, _FP, _I64, C.c_int, _FP, _VP]),
+    "rfv_fm_loss": (C.c_int, [_VP, _FP, _FP, _FP, _I64, _FP, _VP]),
+    "rfv_launch_count": (_I64, [_VP, C.c_int]),
+    "rfv_flops_per_image": (C.c_double, [_VP]),
+    "rfv_debug_activation": (_I64, [_VP, C.c_char_p, _FP, _I64, _VP]),
+    "rfv_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "rfv_profile_report": (C.c_int, [_VP, C.c_char_p, C.c_int]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return str(_build.LIB)
+
+
+def load_library():
+    """dlopen librfv_b200.so and type every entry point.  Raises if it is missing -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"native library {path} is missing: run `python __graft_entry__.py build` (needs nvcc). "
+            "rectified_flow_vision_b200 has no non-CUDA fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.rfv_abi_version() != 1:
+        raise RuntimeError("librfv_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class RfvError(RuntimeError):
+    pass
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load_library().rfv_last_error()
+        raise RfvError(f"rfv error {rc}: {msg.decode() if msg else '?'}")
+
+
+def default_micro_batch(image_size: int) -> int:
+    env = os.environ.get("RFV_MICRO_BATCH")
+    if env:
+        return int(env)
+    return max(8, (256 * 64 * 64) // (image_size * image_size))
+
+
+class Engine:
+    """One native handle: architecture + resolution + device.  Owns packed weights and the activation arena."""
+
+    def __init__(self, arch: Dict, image_size: int, device: torch.device, micro_batch: Optional[int] = None,
+                 flags: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: rectified_flow_vision_b200 runs only on sm_100a GPUs")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        self.image_size = int(image_size)
+        self.in_channels = arch["in_channels"]
+        cfg = RfvConfig()
+        cfg.image_size = image_size
+        cfg.in_channels = arch["in_channels"]
+        cfg.out_channels = arch["out_channels"]
+        cfg.model_channels = arch["model_channels"]
+        mult = list(arch["channel_mult"])
+        if len(mult) > RFV_MAX_LEVELS:
+            raise ValueError("too many levels")
+        cfg.num_levels = len(mult)
+        for i, m in enumerate(mult):
+            cfg.channel_mult[i] = m
+        cfg.num_res_blocks = arch["num_res_blocks"]
+        cfg.num_heads = 4
+        cfg.micro_batch = micro_batch or default_micro_batch(image_size)
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg.flags = int(os.environ.get("RFV_FLAGS", "0")) if flags is None else flags
+        self.micro_batch = cfg.micro_batch
+        h = _VP()
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._versions: Dict[str, tuple] = {}
+        self.tensor_names = []
+        buf = C.create_string_buffer(256)
+        n = _I64()
+        for i in range(self.lib.rfv_num_tensors(self.h)):
+            _check(self.lib.rfv_tensor_info(self.h, i, buf, 256, C.byref(n)))
+            self.tensor_names.append((buf.value.decode(), n.value))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.rfv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ----- helpers ---------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev_f32(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if t.device != self.device and not (t.device.type == "cuda" and self.device.index is None):
+            if t.device.type != "cuda":
+                raise ValueError(f"{name} must live on {self.device} (got {t.device})")
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    # ----- weights ---------------------------------------------------------------------------------------
+    def sync_weights(self, unet: torch.nn.Module, prefix: str = "velocity_net.") -> None:
+        """(Re)upload parameters whose storage or version counter changed since the last upload."""
+        params = dict(unet.named_parameters())
+        with torch.cuda.device(self.device):
+            for full, numel in self.tensor_names:
+                key = full[len(prefix):] if full.startswith(prefix) else full
+                p = params[key]
+                tag = (p.data_ptr(), p._version)
+                if self._versions.get(full) == tag:
+                    continue
+                src = p.detach()
+                if src.device != self.device or src.dtype != torch.float32 or not src.is_contiguous():
+                    src = src.to(self.device, torch.float32).contiguous()
+                if src.numel() != numel:
+                    raise ValueError(f"{full}: expected {numel} elements, got {src.numel()}")
+                _check(self.lib.rfv_set_tensor(self.h, full.encode(), src.data_ptr(), numel, self._stream()))
+                self._versions[full] = tag
+                del src
+
+    def get_tensor(self, name: str, numel: int) -> torch.Tensor:
+        out = torch.empty(numel, dtype=torch.float32, device=self.device)
+        _check(self.lib.rfv_get_tensor(self.h, name.encode(), out.data_ptr(), numel, self._stream()))
+        return out
+
+    # ----- hot path --------------------------------------------------------------------------------------
+    def velocity(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        x = self._dev_f32(x, "x")
+        t = self._dev_f32(t, "t")
+        v = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_velocity(self.h, x.data_ptr(), t.data_ptr(), v.data_ptr(), x.shape[0],
+                                         self._stream()))
+        return v
+
+    def euler_sample(self, noise: torch.Tensor, num_steps: int, save_every: int = 0):
+        """Returns (x_final, traj or None); noise is not modified."""
+        x = self._dev_f32(noise, "noise").clone()
+        traj = None
+        tp = None
+        if save_every and save_every > 0 and num_steps // save_every > 0:
+            traj = torch.empty((num_steps // save_every,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+            tp = traj.data_ptr()
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_euler_sample(self.h, x.data_ptr(), x.shape[0], int(num_steps), tp,
+                                             int(save_every or 0), self._stream()))
+        return x, traj
+
+    def euler_sample_host(self, noise_host: torch.Tensor, num_steps: int, out: Optional[torch.Tensor] = None):
+        """Host fp32 [N,C,S,S] -> host fp32, H2D/D2H inside (pinned buffers are copied asynchronously)."""
+        if noise_host.device.type != "cpu" or noise_host.dtype != torch.float32:
+            raise ValueError("noise_host must be a CPU fp32 tensor")
+        noise_host = noise_host.contiguous()
+        if out is None:
+            out = torch.empty_like(noise_host, pin_memory=noise_host.is_pinned())
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_euler_sample_host(self.h, noise_host.data_ptr(), out.data_ptr(),
+                                                  noise_host.shape[0], int(num_steps)))
+        return out
+
+    def straightness(self, x0: torch.Tensor, x1: torch.Tensor, num_points: int) -> torch.Tensor:
+        x0 = self._dev_f32(x0, "x0")
+        x1 = self._dev_f32(x1, "x1")
+        out = torch.empty(num_points, dtype=torch.float32, device=x0.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_straightness(self.h, x0.data_ptr(), x1.data_ptr(), x0.shape[0], int(num_points),
+                                             out.data_ptr(), self._stream()))
+        return out
+
+    def fm_loss(self, x0: torch.Tensor, x1: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        x0 = self._dev_f32(x0, "x0")
+        x1 = self._dev_f32(x1, "x1")
+        t = self._dev_f32(t, "t")
+        out = torch.empty((), dtype=torch.float32, device=x0.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_fm_loss(self.h, x0.data_ptr(), x1.data_ptr(), t.data_ptr(), x0.shape[0],
+                                        out.data_ptr(), self._stream()))
+        return out
+
+    # ----- introspection ---------------------------------------------------------------------------------
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.rfv_launch_count(self.h, 1 if reset else 0))
+
+    def flops_per_image(self) -> float:
+        return float(self.lib.rfv_flops_per_image(self.h))
+
+    def debug_activation(self, name: str, capacity: int) -> torch.Tensor:
+        out = torch.empty(capacity, dtype=torch.float32, device=self.device)
+        n = self.lib.rfv_debug_activation(self.h, name.encode(), out.data_ptr(), capacity, self._stream())
+        if n < 0:
+            _check(int(n))
+        return out[:n]
+
+    def set_profiling(self, on: bool):
+        _check(self.lib.rfv_set_profiling(self.h, 1 if on else 0))
+
+    def profile_report(self) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.lib.rfv_profile_report(self.h, buf, len(buf)))
+        return buf.value.decode()

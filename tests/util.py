@@ -1,0 +1,69 @@
+"""Shared helpers for the test-suite (CPU and GPU)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def manifest():
+    with open(os.path.join(GOLD, "manifest.json")) as f:
+        return json.load(f)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLD, f"{name}.npz"))
+
+
+def seeded_model(case, device="cpu", cls=None):
+    """The package model with the seed the golden case was generated with (bit-identical weights to the
+    reference constructor under the same seed; the sha in the manifest proves it)."""
+    import rectified_flow_vision_b200 as pkg
+    cls = cls or pkg.BaseFlowModel
+    c = manifest()["cases"][case]
+    torch.manual_seed(c["seed"])
+    m = cls(device="cpu", **c["kwargs"])
+    if device != "cpu":
+        m.device = device
+        m.to(device)
+    return m
+
+
+def state_sha(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def numpy_params(model):
+    return {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+
+
+def spec_for(case):
+    from oracle.unet_oracle import UNetSpec
+    kw = manifest()["cases"][case]["kwargs"]
+    return UNetSpec(model_channels=kw.get("model_channels", 64), channel_mult=kw.get("channel_mult", [1, 2, 4]),
+                    num_res_blocks=kw.get("num_res_blocks", 2))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-30)))
+
+
+def max_rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def psnr(a, b, peak=2.0):
+    mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
+    return 10 * np.log10(peak * peak / max(mse, 1e-30))
