@@ -54,6 +54,7 @@ typedef struct {
 
 #define RFV_FLAG_NO_UMMA   1   /* force the mma.sync implicit-GEMM kernel everywhere (debug / A-B testing) */
 #define RFV_FLAG_NO_GRAPH  2   /* launch kernels directly instead of replaying a captured CUDA graph */
+#define RFV_FLAG_KEEP_ACTS 4   /* never recycle activation buffers, so rfv_debug_activation can read any layer */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int rfv_abi_version(void);

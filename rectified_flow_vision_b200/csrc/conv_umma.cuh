@@ -1,0 +1,248 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores: TMA (tiled, zero-filled halo) -> 128B-swizzled shared
+// memory -> tcgen05.mma with fp32 accumulators in TMEM -> tcgen05.ld epilogue.  Persistent, warp-specialised:
+//   warp 0  TMA producer (one lane)      warp 1  MMA issuer (one lane)      warp 2  TMEM allocator
+//   warps 4-7  epilogue (one TMEM lane = one output pixel per thread)
+// GEMM view: M = 128 output pixels (a bn x bh x bw box of the NHWC tensor), N = BN output channels,
+// K = taps x C_in walked in chunks of 64 channels (one 128-byte swizzle row per pixel).  The im2col gather is done
+// by the TMA unit itself: for tap (dy,dx) the same 4-D box is fetched at (w0+dx-1, h0+dy-1); out-of-bounds
+// coordinates are zero-filled, which is exactly the conv's zero padding.  Stride-2 convs fetch from four
+// parity views of the input (one tensor map each).  A second K segment (1x1 shortcut over a virtual concat of up
+// to two tensors) accumulates into the same TMEM tile, so a ResidualBlock's conv2 + shortcut is one kernel.
+// Replaces nn.Conv2d call sites models/unet.py:38,41,51,76,77,185 (see SURVEY §2.4 for the shapes).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_params.h"
+
+namespace rfv {
+
+struct UmmaGeom {
+    int bw_shift, bh_shift;   // log2 box width / height (pixels); images per box = 128 >> (bw_shift + bh_shift)
+    int tiles_w, tiles_h;     // boxes per image along W and H (1,1 when a box covers whole images)
+    int m_tiles, n_tiles;
+    int cch0, cch1a, cch1b;   // 64-channel chunks per tap of segment 0 / per source of segment 1
+    int taps;                 // 9 or 1
+    int stride2;              // 1: segment 0 reads the four parity maps
+};
+
+constexpr int UMMA_BM = 128;
+constexpr int UMMA_A_BYTES = UMMA_BM * 128;  // 128 pixels x 64 bf16
+
+template <int BN>
+struct UmmaCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = UMMA_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                 const __grid_constant__ CUtensorMap mapW, const ConvParams p, const UmmaGeom g) {
+    using Cfg = UmmaCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::STAGES * UMMA_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapW);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nkb0 = g.taps * g.cch0;
+    const int nkb = nkb0 + g.cch1a + g.cch1b;
+    const int total_tiles = g.m_tiles * g.n_tiles;
+    const int box_shift = g.bw_shift + g.bh_shift;        // log2 pixels per image inside a box
+    const int tiles_per_img = g.tiles_w * g.tiles_h;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+                int n0, h0, w0;
+                if (box_shift >= 7) {
+                    n0 = mt / tiles_per_img;
+                    const int r = mt - n0 * tiles_per_img;
+                    h0 = (r / g.tiles_w) << g.bh_shift;
+                    w0 = (r - (r / g.tiles_w) * g.tiles_w) << g.bw_shift;
+                } else {
+                    n0 = mt << (7 - box_shift);
+                    h0 = 0;
+                    w0 = 0;
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem_a + stage * UMMA_A_BYTES;
+                    uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+                    if (kb < nkb0) {
+                        const int tap = kb / g.cch0, cc = kb - tap * g.cch0;
+                        int dy = 0, dx = 0;
+                        if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; dy -= 1; dx -= 1; }
+                        if (!g.stride2) {
+                            tma_load_4d(sa, &mapA0, &full_bar[stage], cc * 64, w0 + dx, h0 + dy, n0);
+                        } else {
+                            // input row 2*ho + dy: dy=-1 -> odd rows at ho-1; dy=0 -> even rows at ho; dy=+1 -> odd rows at ho
+                            const int ph = (dy == 0) ? 0 : 1, pw = (dx == 0) ? 0 : 1;
+                            const int hh = h0 + (dy < 0 ? -1 : 0), ww = w0 + (dx < 0 ? -1 : 0);
+                            const CUtensorMap* mp = ph ? (pw ? &mapA3 : &mapA2) : (pw ? &mapA1 : &mapA0);
+                            tma_load_4d(sa, mp, &full_bar[stage], cc * 64, ww, hh, n0);
+                        }
+                    } else {
+                        const int k1 = kb - nkb0;
+                        if (k1 < g.cch1a) tma_load_4d(sa, &mapA1, &full_bar[stage], k1 * 64, w0, h0, n0);
+                        else tma_load_4d(sa, &mapA2, &full_bar[stage], (k1 - g.cch1a) * 64, w0, h0, n0);
+                    }
+                    tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, nt * BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = umma_idesc_bf16(UMMA_BM, BN);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * UMMA_A_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)  // 4 x (K = 16) per 64-channel chunk: +32 bytes = +2 in descriptor units
+                        umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;                 // TMEM lane quadrant
+        const int r = q * 32 + lane;            // row of the tile = output pixel
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+            int n, h, w;
+            if (box_shift >= 7) {
+                n = mt / tiles_per_img;
+                const int rr = mt - n * tiles_per_img;
+                h = ((rr / g.tiles_w) << g.bh_shift) + (r >> g.bw_shift);
+                w = ((rr - (rr / g.tiles_w) * g.tiles_w) << g.bw_shift) + (r & ((1 << g.bw_shift) - 1));
+            } else {
+                n = (mt << (7 - box_shift)) + (r >> box_shift);
+                h = (r >> g.bw_shift) & ((1 << g.bh_shift) - 1);
+                w = r & ((1 << g.bw_shift) - 1);
+            }
+            const bool valid = n < p.B;
+            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + ch * 32, acc);
+                tmem_ld_wait();
+                if (ch == BN / 32 - 1) {  // accumulator fully drained into registers: hand the TMEM stage back
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[as]);
+                }
+                const int c0 = nt * BN + ch * 32;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + i);
+                    v[i] = __uint_as_float(acc[i]) + b4.x;
+                    v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
+                    v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
+                    v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
+                }
+                if (p.temb && valid) {
+                    const float* te = p.temb + (size_t)n * p.temb_stride + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(te + i);
+                        v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
+                    }
+                }
+                if (p.resid && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.Cout + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float f[8];
+                        unpack8(rp[i], f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[i * 8 + j] += f[j];
+                    }
+                }
+                if (valid) {
+                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) op[i] = pack8(v + i * 8);
+                }
+                if (p.stats) {
+                    // a warp's 32 rows always lie inside one image (Ho*Wo % 32 == 0)
+                    const int n_w = __shfl_sync(0xffffffffu, n, 0);
+                    const bool v_w = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) {
+                        float s = 0.f, ss = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float x = v[sl * 8 + j]; s += x; ss += x * x; }
+                        s = warp_sum(s);
+                        ss = warp_sum(ss);
+                        if (lane == 0 && v_w) {
+                            float* dst = p.stats + ((size_t)n_w * (p.Cout >> p.slab_shift) + ((c0 + sl * 8) >> p.slab_shift)) * 2;
+                            atomicAdd(dst, s);
+                            atomicAdd(dst + 1, ss);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace rfv

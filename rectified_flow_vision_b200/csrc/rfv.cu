@@ -1,0 +1,926 @@
+// Engine: static launch plan for one UNet velocity evaluation + the Euler integrator + the C ABI (include/rfv.h).
+//
+// The plan is built once per (architecture, resolution, micro-batch): every activation buffer, GroupNorm statistics
+// slice, packed weight and TMA tensor map is allocated / encoded at rfv_create, so the hot path makes no allocation
+// and no host decision beyond iterating a vector of launches.  Wiring follows UNet.forward (models/unet.py:229-275).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "attn.cuh"
+#include "common.cuh"
+#include "conv_mma.cuh"
+#include "conv_params.h"
+#include "conv_umma.cuh"
+#include "misc_kernels.cuh"
+#include "rfv.h"
+
+#define RFV_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace rfv {
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU_CHECK(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess)                                                                                      \
+            return fail(RFV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);  \
+    } while (0)
+#define RFV_TRY(expr)          \
+    do {                       \
+        int _rc = (expr);      \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// device memory bookkeeping
+// ---------------------------------------------------------------------------------------------------------
+struct Act {  // NHWC bf16 activation of the current micro-batch
+    bf16* p = nullptr;
+    int C = 0, H = 0, W = 0;
+    float* stats = nullptr;  // [cap][C/slab][2]
+    size_t bytes = 0;
+    int refs = 0;
+};
+typedef std::shared_ptr<Act> ActP;
+
+struct Param {  // one reference state_dict tensor
+    std::string name;
+    int64_t numel = 0;
+    float* f32 = nullptr;  // device copy in reference layout
+    bool loaded = false;
+    std::function<int(cudaStream_t)> repack;  // refresh derived buffers after upload
+    std::function<int(float*, cudaStream_t)> readback;  // optional: reconstruct fp32 from the packed form
+};
+
+struct RunCtx {
+    int B = 0;               // images in this micro-batch
+    const float* x = nullptr;    // [B,C,S,S] fp32 NCHW input state
+    const float* x1 = nullptr;   // if set: input is (1-t) x + t x1
+    const float* t = nullptr;    // [B] or nullptr (uniform t_scalar)
+    float t_scalar = 0.f;
+    float* out = nullptr;    // v (mode 0) or x in place (mode 1); unused in mode 2
+    float* traj = nullptr;
+    const float* tgt_x0 = nullptr;  // target = tgt_x1 - tgt_x0 for the MSE accumulator
+    const float* tgt_x1 = nullptr;
+    float* mse = nullptr;
+    int mode = 0;
+    float dt = 0.f;
+};
+
+struct Op {
+    std::string label;   // e.g. "conv:enc_blocks.0.conv1"
+    std::string kind;    // kernel class for the profile report
+    double flops = 0;    // algorithmic FLOPs per image
+    std::function<cudaError_t(const RunCtx&, cudaStream_t)> run;
+};
+
+struct ConvLayer {
+    std::string name;
+    int C0 = 0, Cout = 0, ks = 3, stride = 1, ups = 0, C1a = 0, C1b = 0, K0 = 0, Ktot = 0;
+    bf16* w = nullptr;
+    float* bias = nullptr;  // fused (conv bias + shortcut bias)
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace rfv
+
+using namespace rfv;
+
+struct rfv_engine {
+    rfv_config cfg{};
+    int num_sms = 148;
+    int cap = 0;       // micro-batch capacity (even)
+    int slab_shift = 3;
+    int td = 256, sumC = 0;
+    bool keep_acts = false, use_umma = true;
+    EncodeTiledFn encode = nullptr;
+
+    std::vector<void*> allocs;
+    std::vector<Param> params;
+    std::map<std::string, int> param_index;
+    std::vector<std::unique_ptr<ConvLayer>> convs;
+    std::vector<Op> ops;
+    std::map<std::string, ActP> named_acts;
+    std::multimap<size_t, bf16*> free_pool;
+
+    float* stats_arena = nullptr;
+    size_t stats_floats = 0, stats_used = 0;
+    float* temb_act = nullptr;   // [cap][td]
+    float* tproj = nullptr;      // [cap][sumC]
+    float* wcat = nullptr;       // [sumC][td]
+    float* bcat = nullptr;       // [sumC]
+    float* scratch_x = nullptr;  // [cap][C][S][S] fp32 (straightness state)
+    float* xbuf[2] = {nullptr, nullptr};  // host-path double buffers
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_cmp = nullptr;
+    cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{};
+    cudaEvent_t ev_weights = nullptr;  // last parameter upload (made on the caller's stream)
+
+    int64_t launches = 0;
+    double flops_per_image = 0;
+    bool profiling = false;
+    std::map<std::string, std::pair<double, int64_t>> prof;  // kind -> (ms, launches)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::string> prof_kinds;
+
+    ~rfv_engine() {
+        for (void* p : allocs) cudaFree(p);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (ev_weights) cudaEventDestroy(ev_weights);
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        if (s_cmp) cudaStreamDestroy(s_cmp);
+        for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    }
+
+    // ----- allocation -----------------------------------------------------------------------------------
+    template <typename T>
+    int dalloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256));
+        if (e != cudaSuccess) return fail(RFV_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        allocs.push_back(p);
+        *out = reinterpret_cast<T*>(p);
+        return 0;
+    }
+    int new_act(ActP* out, int C, int H, int W, bool with_stats) {
+        auto a = std::make_shared<Act>();
+        a->C = C; a->H = H; a->W = W; a->refs = 1;
+        a->bytes = (size_t)cap * H * W * C * sizeof(bf16);
+        auto it = keep_acts ? free_pool.end() : free_pool.find(a->bytes);
+        if (it != free_pool.end()) { a->p = it->second; free_pool.erase(it); }
+        else RFV_TRY(dalloc(&a->p, a->bytes / sizeof(bf16)));
+        if (with_stats) {
+            size_t n = (size_t)cap * (C >> slab_shift) * 2;
+            if (stats_used + n > stats_floats) return fail(RFV_ERR_NOMEM, "stats arena exhausted");
+            a->stats = stats_arena + stats_used;
+            stats_used += n;
+        }
+        *out = a;
+        return 0;
+    }
+    void release(ActP& a) {
+        if (!a) return;
+        if (--a->refs == 0 && !keep_acts) free_pool.insert({a->bytes, a->p});
+    }
+    static void retain(ActP& a) { a->refs++; }
+
+    // ----- parameters -----------------------------------------------------------------------------------
+    int add_param(const std::string& name, int64_t numel, int* idx) {
+        Param p;
+        p.name = "velocity_net." + name;
+        p.numel = numel;
+        RFV_TRY(dalloc(&p.f32, (size_t)numel));
+        param_index[p.name] = (int)params.size();
+        *idx = (int)params.size();
+        params.push_back(std::move(p));
+        return 0;
+    }
+    float* pf(int idx) { return params[idx].f32; }
+
+    // conv layer with packed bf16 weights [Cout][K0 + C1], K0 = ks*ks*C0; optional shortcut (1x1) segment
+    int add_conv(ConvLayer** out, const std::string& name, int C0, int Cout, int ks, int stride, int ups,
+                 const std::string& sc_name, int C1a, int C1b) {
+        auto L = std::make_unique<ConvLayer>();
+        L->name = name; L->C0 = C0; L->Cout = Cout; L->ks = ks; L->stride = stride; L->ups = ups;
+        L->C1a = C1a; L->C1b = C1b; L->K0 = ks * ks * C0; L->Ktot = L->K0 + C1a + C1b;
+        RFV_TRY(dalloc(&L->w, (size_t)Cout * L->Ktot));
+        RFV_TRY(dalloc(&L->bias, (size_t)Cout));
+        int iw, ib, isw = -1, isb = -1;
+        RFV_TRY(add_param(name + ".weight", (int64_t)Cout * C0 * ks * ks, &iw));
+        RFV_TRY(add_param(name + ".bias", Cout, &ib));
+        ConvLayer* l = L.get();
+        const int C1 = C1a + C1b;
+        if (C1 > 0) {
+            RFV_TRY(add_param(sc_name + ".weight", (int64_t)Cout * C1, &isw));
+            RFV_TRY(add_param(sc_name + ".bias", Cout, &isb));
+        }
+        params[iw].repack = [this, l, iw](cudaStream_t s) {
+            pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "pack launch failed");
+        };
+        params[iw].readback = [this, l](float* dst, cudaStream_t s) {
+            unpack_conv_weight_kernel<<<256, 256, 0, s>>>(l->w, dst, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "unpack launch failed");
+        };
+        auto fuse_bias = [this, l, ib, isb](cudaStream_t s) {
+            add_vec_kernel<<<(l->Cout + 255) / 256, 256, 0, s>>>(pf(ib), isb >= 0 ? pf(isb) : nullptr, l->bias, l->Cout);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "bias launch failed");
+        };
+        params[ib].repack = fuse_bias;
+        if (C1 > 0) {
+            params[isw].repack = [this, l, isw, C1](cudaStream_t s) {
+                pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(isw), l->w, l->Cout, C1, 1, l->Ktot, l->K0);
+                return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "pack launch failed");
+            };
+            params[isw].readback = [this, l, C1](float* dst, cudaStream_t s) {
+                unpack_conv_weight_kernel<<<256, 256, 0, s>>>(l->w, dst, l->Cout, C1, 1, l->Ktot, l->K0);
+                return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "unpack launch failed");
+            };
+            params[isb].repack = fuse_bias;
+        }
+        *out = l;
+        convs.push_back(std::move(L));
+        return 0;
+    }
+
+    // ----- op recording ---------------------------------------------------------------------------------
+    void push(const std::string& kind, const std::string& label, double flops,
+              std::function<cudaError_t(const RunCtx&, cudaStream_t)> fn) {
+        Op op;
+        op.kind = kind; op.label = label; op.flops = flops; op.run = std::move(fn);
+        flops_per_image += flops;
+        ops.push_back(std::move(op));
+    }
+
+    int make_map4(CUtensorMap* m, const bf16* base, int C, int Wd, int Hd, int Nd, size_t sW, size_t sH, size_t sN,
+                  int bw, int bh, int bn) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)Hd, (cuuint64_t)Nd};
+        cuuint64_t strides[3] = {sW * 2, sH * 2, sN * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+        return 0;
+    }
+    int make_map2(CUtensorMap* m, const bf16* base, int K, int rows, int box_rows) {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed with CUresult %d", (int)r);
+        return 0;
+    }
+
+    // Record one convolution.  in0: segment-0 input; sc: raw shortcut sources (0..2); resid: identity residual.
+    int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats) {
+        ConvParams p{};
+        p.out = out->p; p.a0 = in0->p;
+        p.s1a = sc.size() > 0 ? sc[0]->p : nullptr;
+        p.s1b = sc.size() > 1 ? sc[1]->p : nullptr;
+        p.w = L->w; p.bias = L->bias;
+        p.temb = temb_off >= 0 ? tproj + temb_off : nullptr;
+        p.resid = resid ? resid->p : nullptr;
+        p.stats = want_stats ? out->stats : nullptr;
+        p.Ho = out->H; p.Wo = out->W; p.Cout = L->Cout;
+        p.H0 = in0->H; p.W0 = in0->W; p.C0 = L->C0;
+        p.ks = L->ks; p.stride = L->stride; p.ups = L->ups;
+        p.C1a = L->C1a; p.C1b = L->C1b; p.K0 = L->K0; p.Ktot = L->Ktot;
+        p.slab_shift = slab_shift;
+        const double fl = 2.0 * (double)L->Ktot * L->Cout * out->H * out->W;
+        const int HoWo = out->H * out->W;
+        if (HoWo % 32 != 0) return fail(RFV_ERR_INVALID, "conv %s: Ho*Wo=%d must be a multiple of 32", L->name.c_str(), HoWo);
+
+        const bool pow2 = is_pow2(out->W) && is_pow2(out->H);
+        const bool umma_ok = use_umma && pow2 && !L->ups && L->C0 % 64 == 0 && L->C1a % 64 == 0 && L->C1b % 64 == 0 &&
+                             L->Cout % 64 == 0 && HoWo >= 64 && out->W >= 8 && (L->stride == 1 || sc.empty());
+        if (umma_ok) {
+            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; };
+            auto bd = std::make_shared<Bundle>();
+            UmmaGeom& g = bd->g;
+            const int bw = std::min(out->W, 128), bh = std::min(out->H, 128 / bw), bn = 128 / (bw * bh);
+            g.bw_shift = ilog2(bw); g.bh_shift = ilog2(bh);
+            g.tiles_w = out->W / bw; g.tiles_h = out->H / bh;
+            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+            g.taps = L->ks * L->ks; g.stride2 = (L->stride == 2);
+            const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
+            bd->BN = BN;
+            g.n_tiles = L->Cout / BN;
+            const int capN = cap;
+            if (!g.stride2) {
+                RFV_TRY(make_map4(&bd->a0, in0->p, in0->C, in0->W, in0->H, capN, in0->C, (size_t)in0->W * in0->C,
+                                  (size_t)in0->H * in0->W * in0->C, bw, bh, bn));
+                bd->a1 = bd->a0; bd->a2 = bd->a0; bd->a3 = bd->a0;
+                if (sc.size() > 0)
+                    RFV_TRY(make_map4(&bd->a1, sc[0]->p, sc[0]->C, sc[0]->W, sc[0]->H, capN, sc[0]->C, (size_t)sc[0]->W * sc[0]->C,
+                                      (size_t)sc[0]->H * sc[0]->W * sc[0]->C, bw, bh, bn));
+                if (sc.size() > 1)
+                    RFV_TRY(make_map4(&bd->a2, sc[1]->p, sc[1]->C, sc[1]->W, sc[1]->H, capN, sc[1]->C, (size_t)sc[1]->W * sc[1]->C,
+                                      (size_t)sc[1]->H * sc[1]->W * sc[1]->C, bw, bh, bn));
+            } else {
+                // parity views of the (even-sized) input: view(ph,pw)[n,i,j,c] = in[n, 2i+ph, 2j+pw, c]
+                const int C = in0->C, Wi = in0->W, Hi = in0->H;
+                CUtensorMap* mp[4] = {&bd->a0, &bd->a1, &bd->a2, &bd->a3};
+                for (int ph = 0; ph < 2; ++ph)
+                    for (int pw = 0; pw < 2; ++pw)
+                        RFV_TRY(make_map4(mp[ph * 2 + pw], in0->p + ((size_t)ph * Wi + pw) * C, C, Wi / 2, Hi / 2, capN,
+                                          (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
+            }
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            const int sms = num_sms;
+            const int sumC_ = sumC;
+            push("conv_umma", "conv:" + L->name, fl, [p, bd, HoWo, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+                ConvParams q = p;
+                q.B = rc.B;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                UmmaGeom g = bd->g;
+                g.m_tiles = (int)(((size_t)rc.B * HoWo + 127) / 128);
+                const int total = g.m_tiles * g.n_tiles;
+                const int grid = std::min(total, sms);
+                switch (bd->BN) {
+                    case 256:
+                        conv_umma_kernel<256><<<grid, 256, UmmaCfg<256>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        break;
+                    case 128:
+                        conv_umma_kernel<128><<<grid, 256, UmmaCfg<128>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        break;
+                    default:
+                        conv_umma_kernel<64><<<grid, 256, UmmaCfg<64>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                }
+                return cudaGetLastError();
+            });
+        } else {
+            if (L->C0 % 8 != 0 || L->C1a % 8 != 0 || L->C1b % 8 != 0 || L->Cout % 64 != 0)
+                return fail(RFV_ERR_INVALID, "conv %s: unsupported channel counts", L->name.c_str());
+            const int sumC_ = sumC;
+            const int cout = L->Cout;
+            push("conv_mma", "conv:" + L->name, fl, [p, HoWo, sumC_, cout](const RunCtx& rc, cudaStream_t s) {
+                ConvParams q = p;
+                q.B = rc.B;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                dim3 grid((unsigned)(((size_t)rc.B * HoWo + MMA_BM - 1) / MMA_BM), cout / MMA_BN);
+                conv_mma_kernel<<<grid, 256, 0, s>>>(q);
+                return cudaGetLastError();
+            });
+        }
+        return 0;
+    }
+
+    int gn_op(const std::string& name, std::vector<ActP> srcs, ActP out, bool silu) {
+        int ig, ib;
+        const int C = out->C;
+        RFV_TRY(add_param(name + ".weight", C, &ig));
+        RFV_TRY(add_param(name + ".bias", C, &ib));
+        const bf16* xa = srcs[0]->p;
+        const bf16* xb = srcs.size() > 1 ? srcs[1]->p : nullptr;
+        const float* sa = srcs[0]->stats;
+        const float* sb = srcs.size() > 1 ? srcs[1]->stats : nullptr;
+        if (!sa || (xb && !sb)) return fail(RFV_ERR_STATE, "gn %s: source without statistics", name.c_str());
+        const int Ca = srcs[0]->C, Cb = srcs.size() > 1 ? srcs[1]->C : 0;
+        const int HW = out->H * out->W;
+        bf16* o = out->p;
+        const float *gam = pf(ig), *bet = pf(ib);
+        const int ss = slab_shift;
+        if ((C / 8) % (1 << ss) != 0 || Ca % (1 << ss) != 0) return fail(RFV_ERR_INVALID, "gn %s: group/slab mismatch", name.c_str());
+        // ~32 KB of bf16 per block
+        int ppb = std::max(1, 16384 / C);
+        ppb = std::min(ppb, HW);
+        push("gn_apply", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+            dim3 grid((HW + ppb - 1) / ppb, rc.B);
+            gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb, 1e-5f);
+            return cudaGetLastError();
+        });
+        return 0;
+    }
+
+    // ResidualBlock (models/unet.py:55-64).  srcs: 1 tensor, or 2 for the decoder's virtual concat [h, skip].
+    int res_block(const std::string& name, std::vector<ActP> srcs, int Cout, int* temb_cursor, ActP* result) {
+        int Cin = 0;
+        for (auto& a : srcs) Cin += a->C;
+        const int H = srcs[0]->H, W = srcs[0]->W;
+        ActP a1, h, a2, out;
+        RFV_TRY(new_act(&a1, Cin, H, W, false));
+        RFV_TRY(gn_op(name + ".norm1", srcs, a1, true));
+        ConvLayer *c1, *c2;
+        RFV_TRY(add_conv(&c1, name + ".conv1", Cin, Cout, 3, 1, 0, "", 0, 0));
+        RFV_TRY(new_act(&h, Cout, H, W, true));
+        // per-block time projection rows live at [temb_cursor, temb_cursor + Cout) of the concatenated matrix
+        int iw, ib;
+        RFV_TRY(add_param(name + ".time_mlp.1.weight", (int64_t)Cout * td, &iw));
+        RFV_TRY(add_param(name + ".time_mlp.1.bias", Cout, &ib));
+        const int off = *temb_cursor;
+        *temb_cursor += Cout;
+        params[iw].repack = [this, iw, off, Cout](cudaStream_t s) {
+            cudaError_t e = cudaMemcpyAsync(wcat + (size_t)off * td, pf(iw), (size_t)Cout * td * sizeof(float), cudaMemcpyDeviceToDevice, s);
+            return e == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "wcat copy failed");
+        };
+        params[ib].repack = [this, ib, off, Cout](cudaStream_t s) {
+            cudaError_t e = cudaMemcpyAsync(bcat + off, pf(ib), (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, s);
+            return e == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "bcat copy failed");
+        };
+        RFV_TRY(conv_op(c1, a1, {}, nullptr, h, off, true));
+        release(a1);
+        RFV_TRY(new_act(&a2, Cout, H, W, false));
+        RFV_TRY(gn_op(name + ".norm2", {h}, a2, true));
+        release(h);
+        RFV_TRY(new_act(&out, Cout, H, W, true));
+        if (Cin != Cout) {
+            RFV_TRY(add_conv(&c2, name + ".conv2", Cout, Cout, 3, 1, 0, name + ".shortcut", srcs[0]->C, srcs.size() > 1 ? srcs[1]->C : 0));
+            RFV_TRY(conv_op(c2, a2, srcs, nullptr, out, -1, true));
+        } else {
+            RFV_TRY(add_conv(&c2, name + ".conv2", Cout, Cout, 3, 1, 0, "", 0, 0));
+            RFV_TRY(conv_op(c2, a2, {}, srcs[0], out, -1, true));
+        }
+        release(a2);
+        named_acts[name] = out;
+        *result = out;
+        return 0;
+    }
+
+    int build();
+    int run_forward(const RunCtx& rc, cudaStream_t s);
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------------------
+int rfv_engine::build() {
+    const int S = cfg.image_size, mc = cfg.model_channels, nlev = cfg.num_levels, nres = cfg.num_res_blocks;
+    td = 4 * mc;
+    slab_shift = ilog2(mc / 8);
+    std::vector<int> chans(nlev);
+    for (int i = 0; i < nlev; ++i) chans[i] = mc * cfg.channel_mult[i];
+
+    // concatenated time-projection matrix: one row block per ResidualBlock, in forward order
+    sumC = 0;
+    for (int lv = 0; lv < nlev; ++lv) sumC += nres * chans[lv];        // encoder
+    sumC += 2 * chans[nlev - 1];                                       // middle
+    for (int lv = 0; lv < nlev; ++lv) sumC += nres * chans[lv];        // decoder
+    RFV_TRY(dalloc(&wcat, (size_t)sumC * td));
+    RFV_TRY(dalloc(&bcat, (size_t)sumC));
+    RFV_TRY(dalloc(&temb_act, (size_t)cap * td));
+    RFV_TRY(dalloc(&tproj, (size_t)cap * sumC));
+    {   // every stats-carrying tensor holds cap x (C / slab) x 2 floats with C / slab = 8 * channel_mult
+        int mmax = 1;
+        for (int i = 0; i < nlev; ++i) mmax = std::max(mmax, cfg.channel_mult[i]);
+        stats_floats = (size_t)cap * 16 * mmax * (4 * nlev * nres + 2 * nlev + 8);
+    }
+    RFV_TRY(dalloc(&stats_arena, stats_floats));
+
+    // ---- time embedding (models/unet.py:157-162,231) ----
+    int tw1, tb1, tw2, tb2;
+    RFV_TRY(add_param("time_mlp.1.weight", (int64_t)td * mc, &tw1));
+    RFV_TRY(add_param("time_mlp.1.bias", td, &tb1));
+    RFV_TRY(add_param("time_mlp.3.weight", (int64_t)td * td, &tw2));
+    RFV_TRY(add_param("time_mlp.3.bias", td, &tb2));
+    {
+        float *w1 = pf(tw1), *b1 = pf(tb1), *w2 = pf(tw2), *b2 = pf(tb2), *act = temb_act, *proj = tproj, *wc = wcat, *bc = bcat;
+        const int td_ = td, mc_ = mc, sumC_ = sumC;
+        push("temb", "temb:time_mlp", 2.0 * (mc * td + td * td), [=](const RunCtx& rc, cudaStream_t s) {
+            const int rows = rc.t ? rc.B : 1;
+            temb_kernel<<<rows, 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_);
+            return cudaGetLastError();
+        });
+        push("temb", "temb:block_projections", 2.0 * td * sumC, [=](const RunCtx& rc, cudaStream_t s) {
+            const int rows = rc.t ? rc.B : 1;
+            dim3 grid((sumC_ + 63) / 64, (rows + 7) / 8);
+            temb_proj_kernel<<<grid, 256, 8 * td_ * sizeof(float), s>>>(act, wc, bc, proj, rows, td_, sumC_);
+            return cudaGetLastError();
+        });
+    }
+
+    // ---- input conv (models/unet.py:165,234) ----
+    ActP h;
+    {
+        int iw, ib;
+        RFV_TRY(add_param("input_conv.weight", (int64_t)mc * cfg.in_channels * 9, &iw));
+        RFV_TRY(add_param("input_conv.bias", mc, &ib));
+        RFV_TRY(new_act(&h, mc, S, S, true));
+        const float *w = pf(iw), *b = pf(ib);
+        bf16* o = h->p;
+        float* st = h->stats;
+        const int Cin = cfg.in_channels, ss = slab_shift;
+        const int K = Cin * 9;
+        const size_t smem = ((size_t)K * mc + 64 * (K + 1) + (mc / 8) * 2) * sizeof(float);
+        if ((S * S) % 64 != 0) return fail(RFV_ERR_INVALID, "image_size^2 must be a multiple of 64");
+        push("input_conv", "conv:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+            dim3 grid(S * S / 64, rc.B);
+            input_conv_kernel<<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, w, b, o, st, Cin, S, S, mc, ss);
+            return cudaGetLastError();
+        });
+        named_acts["input_conv"] = h;
+    }
+
+    int temb_cursor = 0;
+    std::vector<ActP> skips;
+    int bi = 0, res = S;
+    for (int lv = 0; lv < nlev; ++lv) {
+        for (int r = 0; r < nres; ++r) {
+            ActP out;
+            RFV_TRY(res_block("enc_blocks." + std::to_string(bi), {h}, chans[lv], &temb_cursor, &out));
+            release(h);
+            h = out;
+            ++bi;
+        }
+        retain(h);
+        skips.push_back(h);
+        if (lv < nlev - 1) {
+            ConvLayer* d;
+            RFV_TRY(add_conv(&d, "downsamples." + std::to_string(lv), chans[lv], chans[lv], 3, 2, 0, "", 0, 0));
+            ActP o;
+            res /= 2;
+            RFV_TRY(new_act(&o, chans[lv], res, res, true));
+            RFV_TRY(conv_op(d, h, {}, nullptr, o, -1, true));
+            release(h);
+            h = o;
+            named_acts["downsamples." + std::to_string(lv)] = h;
+        }
+    }
+    // ---- middle ----
+    {
+        ActP out;
+        RFV_TRY(res_block("mid_block1", {h}, h->C, &temb_cursor, &out));
+        release(h);
+        h = out;
+        // attention (models/unet.py:79-100)
+        const int C = h->C, N = res * res, heads = cfg.num_heads, d = C / heads;
+        if (C % heads != 0 || (d != 32 && d != 64)) return fail(RFV_ERR_INVALID, "attention head dim %d unsupported (32 or 64)", d);
+        if (N % 64 != 0) return fail(RFV_ERR_INVALID, "attention needs H*W %% 64 == 0 at the lowest level (got %d)", N);
+        ActP hn, qkv, ao, o2;
+        RFV_TRY(new_act(&hn, C, res, res, false));
+        RFV_TRY(gn_op("mid_attn.norm", {h}, hn, false));
+        ConvLayer *cq, *cp;
+        RFV_TRY(add_conv(&cq, "mid_attn.qkv", C, 3 * C, 1, 1, 0, "", 0, 0));
+        RFV_TRY(new_act(&qkv, 3 * C, res, res, false));
+        RFV_TRY(conv_op(cq, hn, {}, nullptr, qkv, -1, false));
+        release(hn);
+        RFV_TRY(new_act(&ao, C, res, res, false));
+        {
+            const bf16* qp = qkv->p;
+            bf16* op = ao->p;
+            const float sl2 = (1.0f / std::sqrt((float)d)) * 1.4426950408889634f;
+            push("attention", "attn:mid_attn", 4.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
+                dim3 grid(N / 64, heads, rc.B);
+                if (d == 64) attn_kernel<64><<<grid, 128, 0, s>>>(qp, op, N, C, sl2);
+                else attn_kernel<32><<<grid, 128, 0, s>>>(qp, op, N, C, sl2);
+                return cudaGetLastError();
+            });
+        }
+        release(qkv);
+        RFV_TRY(add_conv(&cp, "mid_attn.proj", C, C, 1, 1, 0, "", 0, 0));
+        RFV_TRY(new_act(&o2, C, res, res, true));
+        RFV_TRY(conv_op(cp, ao, {}, h, o2, -1, true));
+        release(ao);
+        release(h);
+        h = o2;
+        named_acts["mid_attn"] = h;
+        RFV_TRY(res_block("mid_block2", {h}, h->C, &temb_cursor, &out));
+        release(h);
+        h = out;
+    }
+    // ---- decoder ----
+    bi = 0;
+    for (int li = 0; li < nlev; ++li) {
+        const int lv = nlev - 1 - li;
+        ActP sk = skips.back();
+        skips.pop_back();
+        ActP out;
+        RFV_TRY(res_block("dec_blocks." + std::to_string(bi), {h, sk}, chans[lv], &temb_cursor, &out));
+        release(h);
+        release(sk);  // the reference taken when the skip was pushed
+        h = out;
+        ++bi;
+        for (int r = 0; r < nres - 1; ++r) {
+            RFV_TRY(res_block("dec_blocks." + std::to_string(bi), {h}, chans[lv], &temb_cursor, &out));
+            release(h);
+            h = out;
+            ++bi;
+        }
+        if (lv > 0) {
+            ConvLayer* u;
+            RFV_TRY(add_conv(&u, "upsamples." + std::to_string(li) + ".1", chans[lv], chans[lv], 3, 1, 1, "", 0, 0));
+            ActP o;
+            res *= 2;
+            RFV_TRY(new_act(&o, chans[lv], res, res, true));
+            RFV_TRY(conv_op(u, h, {}, nullptr, o, -1, true));
+            release(h);
+            h = o;
+            named_acts["upsamples." + std::to_string(li)] = h;
+        }
+    }
+    // ---- output (models/unet.py:223-227,275) fused with the Euler update (models/base_flow.py:170) ----
+    {
+        ActP a;
+        RFV_TRY(new_act(&a, h->C, S, S, false));
+        RFV_TRY(gn_op("output_conv.0", {h}, a, true));
+        release(h);
+        int iw, ib;
+        const int C = a->C, Co = cfg.out_channels;
+        RFV_TRY(add_param("output_conv.2.weight", (int64_t)Co * C * 9, &iw));
+        RFV_TRY(add_param("output_conv.2.bias", Co, &ib));
+        if (Co > 4) return fail(RFV_ERR_INVALID, "out_channels > 4 unsupported");
+        const float *w = pf(iw), *b = pf(ib);
+        const bf16* ap = a->p;
+        const size_t smem = (size_t)(OC_TH + 2) * (OC_TW + 2) * (C * 2 + 16) + (size_t)Co * 9 * C * sizeof(float);
+        CU_CHECK(cudaFuncSetAttribute(output_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        push("output_conv", "conv:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+            dim3 grid((S + OC_TW - 1) / OC_TW, (S + OC_TH - 1) / OC_TH, rc.B);
+            output_conv_kernel<<<grid, 256, smem, s>>>(ap, w, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.mode, rc.dt);
+            return cudaGetLastError();
+        });
+        release(a);
+    }
+    if (temb_cursor != sumC) return fail(RFV_ERR_STATE, "internal: time-projection layout mismatch (%d vs %d)", temb_cursor, sumC);
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
+    return 0;
+}
+
+int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
+    for (auto& p : params)
+        if (!p.loaded) return fail(RFV_ERR_STATE, "parameter %s was never uploaded (rfv_set_tensor)", p.name.c_str());
+    if (rc.B < 1 || rc.B > cap) return fail(RFV_ERR_STATE, "micro-batch %d outside [1,%d]", rc.B, cap);
+    CU_CHECK(cudaMemsetAsync(stats_arena, 0, stats_used * sizeof(float), s));
+    size_t ei = 0;
+    for (auto& op : ops) {
+        if (profiling) {
+            if (ei >= prof_events.size()) {
+                cudaEvent_t a, b;
+                CU_CHECK(cudaEventCreate(&a));
+                CU_CHECK(cudaEventCreate(&b));
+                prof_events.push_back({a, b});
+            }
+            CU_CHECK(cudaEventRecord(prof_events[ei].first, s));
+        }
+        cudaError_t e = op.run(rc, s);
+        if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "launch of %s failed: %s", op.label.c_str(), cudaGetErrorString(e));
+        ++launches;
+        if (profiling) {
+            CU_CHECK(cudaEventRecord(prof_events[ei].second, s));
+            ++ei;
+        }
+    }
+    if (profiling) {
+        CU_CHECK(cudaStreamSynchronize(s));
+        for (size_t i = 0; i < ei; ++i) {
+            float ms = 0.f;
+            CU_CHECK(cudaEventElapsedTime(&ms, prof_events[i].first, prof_events[i].second));
+            auto& slot = prof[ops[i].kind + " " + ops[i].label];
+            slot.first += ms;
+            slot.second += 1;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+RFV_EXPORT int rfv_abi_version(void) { return RFV_ABI_VERSION; }
+RFV_EXPORT const char* rfv_last_error(void) { return g_err; }
+
+RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
+    if (!cfg || !out) return fail(RFV_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_levels < 1 || cfg->num_levels > RFV_MAX_LEVELS) return fail(RFV_ERR_INVALID, "num_levels out of range");
+    if (cfg->model_channels < 64 || cfg->model_channels % 64 != 0 || !is_pow2(cfg->model_channels / 8))
+        return fail(RFV_ERR_INVALID, "model_channels must be 64, 128, 256, ... (got %d)", cfg->model_channels);
+    if (cfg->in_channels < 1 || cfg->in_channels > 4 || cfg->out_channels < 1 || cfg->out_channels > 4)
+        return fail(RFV_ERR_INVALID, "in/out channels must be in [1,4]");
+    if (cfg->num_res_blocks < 1 || cfg->micro_batch < 1) return fail(RFV_ERR_INVALID, "num_res_blocks / micro_batch must be >= 1");
+    const int down = 1 << (cfg->num_levels - 1);
+    if (cfg->image_size % down != 0 || cfg->image_size / down < 8)
+        return fail(RFV_ERR_INVALID, "image_size %d too small for %d levels (lowest level must be >= 8x8)", cfg->image_size, cfg->num_levels);
+    CU_CHECK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(RFV_ERR_INVALID, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    auto e = std::make_unique<rfv_engine>();
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    e->cap = (cfg->micro_batch + 1) & ~1;
+    e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
+    e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
+    CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+        e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    RFV_TRY(e->build());
+    const size_t xin = (size_t)e->cap * cfg->in_channels * cfg->image_size * cfg->image_size;
+    RFV_TRY(e->dalloc(&e->scratch_x, xin));
+    RFV_TRY(e->dalloc(&e->xbuf[0], xin));
+    RFV_TRY(e->dalloc(&e->xbuf[1], xin));
+    CU_CHECK(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamCreateWithFlags(&e->s_cmp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_CHECK(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+    }
+    *out = e.release();
+    return 0;
+}
+
+RFV_EXPORT int rfv_destroy(rfv_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    delete h;
+    return 0;
+}
+
+RFV_EXPORT int rfv_num_tensors(rfv_handle h) { return h ? (int)h->params.size() : 0; }
+
+RFV_EXPORT int rfv_tensor_info(rfv_handle h, int index, char* name_buf, int name_buf_len, int64_t* numel) {
+    if (!h || index < 0 || index >= (int)h->params.size()) return fail(RFV_ERR_INVALID, "tensor index out of range");
+    if (name_buf && name_buf_len > 0) snprintf(name_buf, name_buf_len, "%s", h->params[index].name.c_str());
+    if (numel) *numel = h->params[index].numel;
+    return 0;
+}
+
+RFV_EXPORT int rfv_set_tensor(rfv_handle h, const char* name, const float* dev_ptr, int64_t numel, void* stream) {
+    if (!h || !name || !dev_ptr) return fail(RFV_ERR_INVALID, "null argument");
+    auto it = h->param_index.find(name);
+    if (it == h->param_index.end()) return fail(RFV_ERR_INVALID, "unknown tensor '%s'", name);
+    Param& p = h->params[it->second];
+    if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaMemcpyAsync(p.f32, dev_ptr, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (p.repack) RFV_TRY(p.repack(s));
+    p.loaded = true;
+    CU_CHECK(cudaEventRecord(h->ev_weights, s));
+    return 0;
+}
+
+RFV_EXPORT int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream) {
+    if (!h || !name || !dev_ptr) return fail(RFV_ERR_INVALID, "null argument");
+    auto it = h->param_index.find(name);
+    if (it == h->param_index.end()) return fail(RFV_ERR_INVALID, "unknown tensor '%s'", name);
+    Param& p = h->params[it->second];
+    if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements", name, (long long)p.numel);
+    if (!p.loaded) return fail(RFV_ERR_STATE, "tensor '%s' not loaded", name);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.readback) return p.readback(dev_ptr, s);
+    CU_CHECK(cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+static size_t image_elems(rfv_handle h) { return (size_t)h->cfg.in_channels * h->cfg.image_size * h->cfg.image_size; }
+
+RFV_EXPORT int rfv_velocity(rfv_handle h, const float* x, const float* t, float* v, int64_t batch, void* stream) {
+    if (!h || !x || !t || !v || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    if (h->cfg.in_channels != h->cfg.out_channels) return fail(RFV_ERR_INVALID, "in_channels != out_channels");
+    const size_t ie = image_elems(h);
+    for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
+        RunCtx rc;
+        rc.B = (int)std::min<int64_t>(h->cap, batch - b0);
+        rc.x = x + b0 * ie; rc.t = t + b0; rc.out = v + b0 * ie; rc.mode = 0;
+        RFV_TRY(h->run_forward(rc, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj, int save_every, size_t traj_stride,
+                       const float* tx0, const float* tx1, float* mse, cudaStream_t s) {
+    const double dt = 1.0 / num_steps;  // Python double, like models/base_flow.py:158
+    for (int i = 0; i < num_steps; ++i) {
+        RunCtx rc;
+        rc.B = B; rc.x = x; rc.out = x; rc.mode = 1;
+        rc.t = nullptr; rc.t_scalar = (float)(i * dt); rc.dt = (float)dt;
+        if (traj && save_every > 0 && (i + 1) % save_every == 0) rc.traj = traj + (size_t)((i + 1) / save_every - 1) * traj_stride;
+        if (mse) { rc.tgt_x0 = tx0; rc.tgt_x1 = tx1; rc.mse = mse + i; }
+        RFV_TRY(h->run_forward(rc, s));
+    }
+    return 0;
+}
+
+RFV_EXPORT int rfv_euler_sample(rfv_handle h, float* x, int64_t batch, int num_steps, float* traj, int save_every, void* stream) {
+    if (!h || !x || batch < 1 || num_steps < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    const size_t ie = image_elems(h);
+    for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
+        const int B = (int)std::min<int64_t>(h->cap, batch - b0);
+        RFV_TRY(euler_chunk(h, x + b0 * ie, B, num_steps, traj ? traj + b0 * ie : nullptr, save_every, (size_t)batch * ie, nullptr,
+                            nullptr, nullptr, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, float* out_host, int64_t n, int num_steps) {
+    if (!h || !noise_host || !out_host || n < 1 || num_steps < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    const size_t ie = image_elems(h);
+    CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_weights, 0));  // uploads were enqueued on the caller's stream
+    int64_t idx = 0;
+    for (int64_t b0 = 0; b0 < n; b0 += h->cap, ++idx) {
+        const int B = (int)std::min<int64_t>(h->cap, n - b0);
+        const int k = (int)(idx & 1);
+        // buffer k is free once its previous result has left the device
+        if (idx >= 2) CU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[k], 0));
+        CU_CHECK(cudaMemcpyAsync(h->xbuf[k], noise_host + b0 * ie, (size_t)B * ie * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+        CU_CHECK(cudaEventRecord(h->ev_in[k], h->s_h2d));
+        CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
+        RFV_TRY(euler_chunk(h, h->xbuf[k], B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
+        CU_CHECK(cudaEventRecord(h->ev_done[k], h->s_cmp));
+        CU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[k], 0));
+        CU_CHECK(cudaMemcpyAsync(out_host + b0 * ie, h->xbuf[k], (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        CU_CHECK(cudaEventRecord(h->ev_out[k], h->s_d2h));
+    }
+    CU_CHECK(cudaStreamSynchronize(h->s_d2h));
+    CU_CHECK(cudaStreamSynchronize(h->s_cmp));
+    return 0;
+}
+
+RFV_EXPORT int rfv_straightness(rfv_handle h, const float* x0, const float* x1, int64_t batch, int num_points, float* dev_out, void* stream) {
+    if (!h || !x0 || !x1 || !dev_out || batch < 1 || num_points < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ie = image_elems(h);
+    CU_CHECK(cudaMemsetAsync(dev_out, 0, (size_t)num_points * sizeof(float), s));
+    for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
+        const int B = (int)std::min<int64_t>(h->cap, batch - b0);
+        CU_CHECK(cudaMemcpyAsync(h->scratch_x, x0 + b0 * ie, (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        RFV_TRY(euler_chunk(h, h->scratch_x, B, num_points, nullptr, 0, 0, x0 + b0 * ie, x1 + b0 * ie, dev_out, s));
+    }
+    scale_kernel<<<(num_points + 255) / 256, 256, 0, s>>>(dev_out, num_points, 1.0f / (float)((double)batch * ie));
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+RFV_EXPORT int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch, float* loss_out, void* stream) {
+    if (!h || !x0 || !x1 || !t || !loss_out || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ie = image_elems(h);
+    CU_CHECK(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
+    for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
+        RunCtx rc;
+        rc.B = (int)std::min<int64_t>(h->cap, batch - b0);
+        rc.x = x0 + b0 * ie; rc.x1 = x1 + b0 * ie; rc.t = t + b0; rc.mode = 2;
+        rc.tgt_x0 = x0 + b0 * ie; rc.tgt_x1 = x1 + b0 * ie; rc.mse = loss_out;
+        RFV_TRY(h->run_forward(rc, s));
+    }
+    scale_kernel<<<1, 32, 0, s>>>(loss_out, 1, 1.0f / (float)((double)batch * ie));
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+RFV_EXPORT int64_t rfv_launch_count(rfv_handle h, int reset) {
+    if (!h) return 0;
+    const int64_t v = h->launches;
+    if (reset) h->launches = 0;
+    return v;
+}
+
+RFV_EXPORT double rfv_flops_per_image(rfv_handle h) { return h ? h->flops_per_image : 0.0; }
+
+RFV_EXPORT int64_t rfv_debug_activation(rfv_handle h, const char* name, float* dev_out, int64_t capacity, void* stream) {
+    if (!h || !name || !dev_out) return fail(RFV_ERR_INVALID, "null argument");
+    if (!h->keep_acts) return fail(RFV_ERR_STATE, "engine was created without the keep-activations flag (4)");
+    auto it = h->named_acts.find(name);
+    if (it == h->named_acts.end()) return fail(RFV_ERR_INVALID, "unknown activation '%s'", name);
+    const Act& a = *it->second;
+    const int64_t per_img = (int64_t)a.C * a.H * a.W;
+    const int B = (int)std::min<int64_t>(h->cap, capacity / per_img);
+    if (B < 1) return fail(RFV_ERR_INVALID, "capacity too small");
+    nhwc_to_nchw_kernel<<<512, 256, 0, (cudaStream_t)stream>>>(a.p, dev_out, B, a.C, a.H * a.W);
+    if (cudaGetLastError() != cudaSuccess) return fail(RFV_ERR_CUDA, "debug copy launch failed");
+    return (int64_t)B * per_img;
+}
+
+RFV_EXPORT int rfv_set_profiling(rfv_handle h, int enabled) {
+    if (!h) return fail(RFV_ERR_INVALID, "null handle");
+    h->profiling = enabled != 0;
+    if (enabled) h->prof.clear();
+    return 0;
+}
+
+RFV_EXPORT int rfv_profile_report(rfv_handle h, char* buf, int buf_len) {
+    if (!h || !buf || buf_len < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    std::string out;
+    char line[512];
+    for (auto& kv : h->prof) {
+        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+        out += line;
+    }
+    snprintf(buf, buf_len, "%s", out.c_str());
+    return 0;
+}

@@ -104,6 +104,8 @@ class Engine:
             raise RuntimeError("no CUDA device: rectified_flow_vision_b200 runs only on sm_100a GPUs")
         self.lib = load_library()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.image_size = int(image_size)
         self.in_channels = arch["in_channels"]
         cfg = RfvConfig()
@@ -148,9 +150,10 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _dev_f32(self, t: torch.Tensor, name: str) -> torch.Tensor:
-        if t.device != self.device and not (t.device.type == "cuda" and self.device.index is None):
-            if t.device.type != "cuda":
-                raise ValueError(f"{name} must live on {self.device} (got {t.device})")
+        if t.device.type != "cuda":
+            raise ValueError(f"{name} must be a CUDA tensor on {self.device} (got {t.device}); there is no CPU path")
+        if t.device != self.device:
+            t = t.to(self.device)
         if t.dtype != torch.float32:
             t = t.float()
         return t.contiguous()

@@ -142,6 +142,8 @@ class UNet(_Node):
                 "rectified_flow_vision_b200 has no CPU path: the velocity field runs only through the sm_100a "
                 f"CUDA library (got device {dev}).")
         eng = self._engine
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         if eng is None or eng.image_size != image_size or eng.device != dev:
             eng = _engine.Engine(self.arch(), image_size, dev)
             self._engine = eng
@@ -149,7 +151,7 @@ class UNet(_Node):
         return eng
 
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+        if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
                 "training-mode forward with autograd is not part of the native path yet (SURVEY §8 a15); "
                 "call under torch.no_grad() / eval().")

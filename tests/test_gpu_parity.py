@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden vectors and the CPU oracle.
+
+Tolerances (floating point, bf16 storage / fp32 accumulate; SURVEY.md §7 'bf16 tolerance'):
+  * vs the reference's fp32 outputs (tests/golden): velocity rel-L2 <= 3e-2, max|d|/max|ref| <= 5e-2;
+    N-step samples PSNR >= 45 dB (peak 2.0).  PyTorch's own bf16 autocast sits at 1.6e-2 / 1.9e-2 / 50 dB.
+  * vs the oracle run under the SAME rounding policy (oracle.BF16_POLICY): rel-L2 <= 8e-3 -- this is the check
+    that catches kernel bugs, since both sides round at the same points.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_REF_L2, TOL_REF_MAX, TOL_POLICY_L2, MIN_PSNR = 3e-2, 5e-2, 8e-3, 45.0
+
+
+def _engine(case, flags=0, micro_batch=4):
+    from rectified_flow_vision_b200 import engine as E
+    m = util.seeded_model(case, device="cuda:0")
+    size = util.manifest()["cases"][case]["kwargs"]["image_size"]
+    eng = E.Engine(m.velocity_net.arch(), size, torch.device("cuda:0"), micro_batch=micro_batch, flags=flags)
+    eng.sync_weights(m.velocity_net)
+    return m, eng
+
+
+@pytest.fixture(scope="module", params=["small32", "default64"])
+def case(request):
+    return request.param
+
+
+def test_native_library_is_loaded():
+    from rectified_flow_vision_b200 import engine as E
+    E.load_library()
+    with open("/proc/self/maps") as f:
+        assert "librfv_b200.so" in f.read()
+
+
+def test_weight_pack_roundtrip(case):
+    m, eng = _engine(case)
+    for name, p in m.state_dict().items():
+        if name.endswith("conv1.weight") or name.endswith("shortcut.weight") or name.endswith("qkv.weight"):
+            back = eng.get_tensor(name, p.numel()).view_as(p)
+            assert torch.equal(back, p.bfloat16().float()), name
+
+
+def test_velocity_vs_reference_and_oracle(case):
+    from oracle import unet_oracle as O
+    m, eng = _engine(case)
+    g = util.golden(case)
+    x = torch.from_numpy(g["x"]).cuda()
+    t = torch.from_numpy(g["t"]).cuda()
+    v = m(x, t).cpu().numpy()
+    assert np.isfinite(v).all()
+    assert util.rel_l2(v, g["v"]) <= TOL_REF_L2
+    assert util.max_rel(v, g["v"]) <= TOL_REF_MAX
+    v_pol = O.unet_forward(util.numpy_params(m), g["x"], g["t"], util.spec_for(case), policy=O.BF16_POLICY)
+    assert util.rel_l2(v, v_pol) <= TOL_POLICY_L2
+
+
+def test_layers_vs_oracle(case):
+    from oracle import unet_oracle as O
+    m, eng = _engine(case, flags=4)
+    g = util.golden(case)
+    taps = {}
+    O.unet_forward(util.numpy_params(m), g["x"], g["t"], util.spec_for(case), policy=O.BF16_POLICY, taps=taps)
+    eng.velocity(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda())
+    for name, ref in taps.items():
+        got = eng.debug_activation(name, ref.size).cpu().numpy().reshape(ref.shape)
+        assert util.rel_l2(got, ref) <= TOL_POLICY_L2, name
+
+
+def test_tcgen05_and_mma_sync_kernels_agree(case):
+    g = util.golden(case)
+    x = torch.from_numpy(g["x"]).cuda()
+    t = torch.from_numpy(g["t"]).cuda()
+    _, e1 = _engine(case, flags=0)
+    _, e2 = _engine(case, flags=1)
+    v1 = e1.velocity(x, t).cpu().numpy()
+    v2 = e2.velocity(x, t).cpu().numpy()
+    assert util.rel_l2(v1, v2) <= 4e-3
+
+
+@pytest.mark.parametrize("steps", [1, 2, 4, 8])
+def test_euler_samples_vs_reference(case, steps):
+    m, _ = _engine(case)
+    g = util.golden(case)
+    noise = torch.from_numpy(g["x"]).cuda()
+    keep = noise.clone()
+    out = m.sample(noise=noise, num_steps=steps)
+    assert torch.equal(noise, keep), "sample() must not modify the caller's noise"
+    assert not m.training
+    out = out.cpu().numpy()
+    assert util.psnr(out, g[f"sample_{steps}"]) >= MIN_PSNR
+    assert util.rel_l2(out, g[f"sample_{steps}"]) <= TOL_REF_L2
+
+
+def test_trajectory_api(case):
+    m, _ = _engine(case)
+    g = util.golden(case)
+    noise = torch.from_numpy(g["x"]).cuda()
+    traj = m.sample_with_trajectory(noise, num_steps=4, save_every=2)
+    assert len(traj) == 3
+    for a, b in zip(traj, g["traj_4_2"]):
+        assert util.psnr(a.cpu().numpy(), b) >= MIN_PSNR
+    full = m.sample(noise=noise, num_steps=4, return_trajectory=True)
+    assert len(full) == 5
+    assert torch.allclose(full[2], traj[1], atol=1e-5) and torch.allclose(full[4], traj[2], atol=1e-5)
+
+
+def test_loss_and_straightness(case):
+    import rectified_flow_vision_b200 as pkg
+    info = util.manifest()["cases"][case]
+    m = util.seeded_model(case, device="cuda:0", cls=pkg.RectifiedFlowModel)
+    g = util.golden(case)
+    x0, x1, t = (torch.from_numpy(g[k]).cuda() for k in ("x", "x1", "t"))
+    loss = float(m._engine(x0.shape[-1]).fm_loss(x0, x1, t))
+    assert abs(loss - info["fm_loss"]) <= 2e-2 * info["fm_loss"]
+    s = m.compute_straightness(x0, x1, num_points=3)
+    assert abs(s - info["straightness_3"]) <= 2e-2 * info["straightness_3"]
+    xt, target = m.get_interpolation(x0, x1, t)
+    np.testing.assert_allclose(xt.cpu().numpy(), g["xt"], atol=1e-6)
+    np.testing.assert_allclose(target.cpu().numpy(), g["target"], atol=0)
+
+
+def test_micro_batching_is_invisible():
+    """Images are independent ODE solves: results must not depend on how the batch is cut."""
+    m, eng_small = _engine("small32", micro_batch=2)
+    _, eng_big = _engine("small32", micro_batch=16)
+    gen = torch.Generator().manual_seed(7)
+    noise = torch.randn(7, 3, 32, 32, generator=gen).cuda()
+    a, _ = eng_small.euler_sample(noise, 2)
+    b, _ = eng_big.euler_sample(noise, 2)
+    assert util.rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 2e-3
+
+
+def test_host_path_and_pair_generation():
+    import rectified_flow_vision_b200 as pkg
+    m, eng = _engine("small32", micro_batch=4)
+    gen = torch.Generator().manual_seed(3)
+    noise = torch.randn(10, 3, 32, 32, generator=gen)
+    dev_out, _ = eng.euler_sample(noise.cuda(), 3)
+    host_out = eng.euler_sample_host(noise.pin_memory(), 3)
+    assert host_out.device.type == "cpu"
+    assert util.rel_l2(host_out.numpy(), dev_out.cpu().numpy()) <= 2e-3
+    x0, x1 = pkg.generate_reflow_pairs(m, num_pairs=10, num_steps=3, noise=noise)
+    assert x0.device.type == "cpu" and x1.device.type == "cpu" and x0.shape == x1.shape == (10, 3, 32, 32)
+    assert torch.equal(x0, noise)
+    assert util.rel_l2(x1.numpy(), dev_out.cpu().numpy()) <= 2e-3
+
+
+def test_errors_are_loud():
+    from rectified_flow_vision_b200 import engine as E
+    m, eng = _engine("small32")
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 3, 32, 16).cuda(), torch.zeros(2).cuda())
+    with pytest.raises(E.RfvError):
+        E.Engine(dict(in_channels=3, model_channels=48, out_channels=3, channel_mult=[1, 2], num_res_blocks=1), 32,
+                 torch.device("cuda:0"))
