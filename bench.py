@@ -1,0 +1,320 @@
+"""Benchmark of the Euler-integration hot path on B200 (contract: see the task prompt / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs-per-step P]
+
+Headline workload (BASELINE.json configs[1]): reflow pair generation -- 100-step Euler through the default UNet
+(64x64x3, 11.26 M parameters, seeded random-init weights because the reference's checkpoints are not in its
+checkout) over host-seeded N(0,1) noise, sharded along the batch over the ranks.  One "step" = one batch of
+P pairs per GPU integrated for 100 Euler steps.  metric = pairs/s, whole job.
+
+Also reported on rank 0 (N=1): Euler sampling images/s at 1/2/4/8 steps for batch 64 (configs[0]) and batch 4096
+(configs[2]), the per-kernel-class time split, the tcgen05 conv roofline, and the CPU baseline (oracle port timed
+on the host cores on a bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGE, CH, EULER_STEPS, TOTAL_PAIRS = 64, 3, 100, 65536
+FLOPS_PER_IMG_STEP = 12.7636e9  # SURVEY.md §8d / BASELINE.md §3 (algorithmic, 64x64)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm (oracle port on the host cores)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_port_pairs_per_sec(sample_images: int, sample_steps: int, repeats: int = 1):
+    """Time the functional-PyTorch port of the reference path on the host CPU, all threads, on a bounded sample:
+    `sample_images` noises integrated for `sample_steps` Euler steps (cost is linear in steps -- reference CSV,
+    results/benchmark_results.csv:2-9 -- so pairs/s at 100 steps = images*steps/s / 100)."""
+    import torch
+    from oracle import torch_port
+    import rectified_flow_vision_b200 as pkg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = pkg.BaseFlowModel(device="cpu")
+    P = {k: v.detach() for k, v in m.state_dict().items()}
+    noise = torch.randn(sample_images, CH, IMAGE, IMAGE, generator=torch.Generator().manual_seed(42))
+    torch_port.euler_sample(P, noise[:2], 1)  # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        torch_port.euler_sample(P, noise, sample_steps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    img_steps_per_s = sample_images * sample_steps / best
+    return img_steps_per_s / EULER_STEPS, cores, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    imgs, steps = 16, 4
+    times = []
+    pps = None
+    for i in range(args.warmup + args.steps):
+        v, cores, dt = cpu_port_pairs_per_sec(imgs, steps)
+        if i >= args.warmup:
+            times.append(dt)
+            pps = v if pps is None else max(pps, v)
+    mean_dt = sum(times) / len(times)
+    value = (imgs * steps / mean_dt) / EULER_STEPS
+    sample = f"{imgs} seeded noises x {steps} Euler steps per step, scaled linearly to {EULER_STEPS} steps"
+    line = {"impl": "reference", "metric": "reflow_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, default_mb()),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def default_mb():
+    from rectified_flow_vision_b200.engine import default_micro_batch
+    return default_micro_batch(IMAGE)
+
+
+def workload_config(args, micro_batch):
+    return {"workload": f"reflow pair generation: default UNet 64x64x3 (base_flow_final.pt architecture, seeded random-init "
+                        f"weights), {EULER_STEPS}-step Euler, {args.pairs_per_step} seeded noises per GPU per step out of the "
+                        f"{TOTAL_PAIRS}-pair job, batch-sharded over {args.gpus} GPU(s)",
+            "pairs_per_step_per_gpu": args.pairs_per_step, "euler_steps": EULER_STEPS, "image": [CH, IMAGE, IMAGE],
+            "micro_batch": micro_batch, "parallelism": f"dp{args.gpus} (batch shards, no data-path collective)",
+            "l2_policy": "inputs larger than L2: per-step activation traffic >> 126 MB; fresh noise buffer each step"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import rectified_flow_vision_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    torch.manual_seed(0)  # identical replicas on every rank
+    model = pkg.BaseFlowModel(device=f"cuda:{local}")
+    model.eval()
+    eng = model._engine()
+    P = args.pairs_per_step
+    gen = torch.Generator().manual_seed(42 + rank)
+    n_bufs = args.warmup + args.steps
+    host_noise = [torch.randn(P, CH, IMAGE, IMAGE, generator=gen).pin_memory() for _ in range(min(n_bufs, 4))]
+    dev_noise = [h.to(dev) for h in host_noise]
+
+    # ---- value: inputs resident in HBM, device-timed ----
+    for i in range(args.warmup):
+        eng.euler_sample(dev_noise[i % len(dev_noise)], EULER_STEPS)
+    barrier()
+    eng.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        eng.euler_sample(dev_noise[(args.warmup + i) % len(dev_noise)], EULER_STEPS)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count(reset=True)
+    value = world * P * args.steps / (ms / 1e3)
+
+    # ---- e2e: the public API with host buffers (H2D + D2H inside the timed region) ----
+    e2e_steps = max(1, min(args.steps, 2))
+    out = pkg.generate_reflow_pairs(model, num_pairs=P, num_steps=EULER_STEPS, noise=host_noise[0])  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        x0, x1 = pkg.generate_reflow_pairs(model, num_pairs=P, num_steps=EULER_STEPS, noise=host_noise[i % len(host_noise)])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * P * e2e_steps / e2e_s
+    img_bytes = P * CH * IMAGE * IMAGE * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    line = {"metric": "reflow_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, default_mb()),
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
+                    "api": "generate_reflow_pairs(model, num_pairs, num_steps=100, noise=<pinned host tensor>)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "unet_flops_fraction_of_peak": {
+                "achieved_tflops": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world,
+                "of_sustained": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["sustained"],
+                "of_burst": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["burst"], "peaks": pk["source"]}}
+
+    if world == 1:
+        # ---- per-kernel-class split + roofline of the dominant kernel, measured live with CUDA events ----
+        mb = eng.micro_batch
+        x = dev_noise[0][:mb].clone()
+        eng.set_profiling(True)
+        for _ in range(3):
+            eng.euler_sample(x, 1)
+        rep = eng.profile_report()
+        eng.set_profiling(False)
+        kinds = {}
+        for ln in rep.strip().splitlines():
+            key, ms_tot, n, fl_img = ln.split("\t")
+            kind, label = key.split(" ", 1)
+            k = kinds.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0})
+            k["ms"] += float(ms_tot) / 3.0
+            k["launches"] += int(n) // 3
+            k["gflop_per_image"] += float(fl_img) / 1e9
+        tot_ms = sum(k["ms"] for k in kinds.values())
+        for k in kinds.values():
+            k["share"] = k["ms"] / tot_ms
+        line["kernel_split_ms_per_forward"] = {"micro_batch": mb, **{k: v for k, v in kinds.items()}}
+        if "conv_umma" in kinds:
+            # algorithmic FLOPs (2*MACs, rfv_profile_report) of the convolutions the tcgen05 kernel executed
+            fl = kinds["conv_umma"]["gflop_per_image"] * 1e9 * mb
+            secs = kinds["conv_umma"]["ms"] / 1e3
+            ach = fl / secs / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_umma_kernel<BN> (tcgen05 implicit-GEMM convs, all launches of one forward)",
+                                "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
+                                "frac_of_burst": ach / pk["burst"], "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
+                                "traffic": None, "flops_per_forward": fl, "ms_per_forward": kinds["conv_umma"]["ms"]}
+        # ---- sampling throughput, configs[0] (B=64) and configs[2] (B=4096) ----
+        samp = {}
+        for bsz, reps in ((64, 5), (4096, 2)):
+            nz = torch.randn(bsz, CH, IMAGE, IMAGE, generator=torch.Generator().manual_seed(1)).to(dev)
+            for steps in (1, 2, 4, 8):
+                if bsz == 4096 and steps > 2:
+                    continue
+                eng.euler_sample(nz, steps)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    eng.euler_sample(nz, steps)
+                b.record()
+                torch.cuda.synchronize()
+                samp[f"b{bsz}_steps{steps}"] = bsz * reps / (a.elapsed_time(b) / 1e3)
+        line["sampling_images_per_sec"] = samp
+        # ---- CPU baseline: the oracle port on this host's cores, bounded sample ----
+        try:
+            v, cores, secs = cpu_port_pairs_per_sec(16, 4)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                    "sample": f"16 seeded noises x 4 Euler steps ({secs:.1f} s), scaled linearly to {EULER_STEPS} steps; "
+                                              "functional-PyTorch fp32 port of the reference path (oracle/torch_port.py)"}
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "error": str(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-step", type=int, default=512)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

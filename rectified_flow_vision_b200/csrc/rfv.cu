@@ -917,8 +917,11 @@ RFV_EXPORT int rfv_profile_report(rfv_handle h, char* buf, int buf_len) {
     if (!h || !buf || buf_len < 1) return fail(RFV_ERR_INVALID, "bad argument");
     std::string out;
     char line[512];
-    for (auto& kv : h->prof) {
-        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+    std::map<std::string, double> flops;
+    for (auto& op : h->ops) flops[op.kind + " " + op.label] = op.flops;
+    for (auto& kv : h->prof) {  // "<kind> <label>\t<total ms>\t<launches>\t<algorithmic FLOPs per image>"
+        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\t%.1f\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second,
+                 flops[kv.first]);
         out += line;
     }
     snprintf(buf, buf_len, "%s", out.c_str());

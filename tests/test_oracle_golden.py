@@ -87,3 +87,18 @@ def test_bf16_policy_is_close_to_fp32(case):
     v = O.unet_forward(P, g["x"], g["t"], spec, policy=O.BF16_POLICY)
     assert util.rel_l2(v, g["v"]) < 3e-2
     assert util.max_rel(v, g["v"]) < 5e-2
+
+
+def test_torch_port_matches_reference(case):
+    """The functional-PyTorch port used as the CPU baseline is pinned against the same golden vectors."""
+    import torch
+    from oracle import torch_port
+    name, P, g, spec, info = case
+    kw = info["kwargs"]
+    arch = dict(model_channels=kw.get("model_channels", 64), channel_mult=tuple(kw.get("channel_mult", [1, 2, 4])),
+                num_res_blocks=kw.get("num_res_blocks", 2))
+    Pt = {k: torch.from_numpy(v) for k, v in P.items()}
+    v = torch_port.unet_forward(Pt, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), **arch).numpy()
+    assert util.rel_l2(v, g["v"]) < 1e-5
+    x = torch_port.euler_sample(Pt, torch.from_numpy(g["x"]), 2, **arch).numpy()
+    assert util.rel_l2(x, g["sample_2"]) < 1e-5
