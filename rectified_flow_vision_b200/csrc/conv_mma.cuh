@@ -119,11 +119,9 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const ConvParams p) {
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
         const int col = n0 + warp_n * 32 + nt * 8 + tq * 2;
-        float add0 = p.bias[col], add1 = p.bias[col + 1];
-        if (p.temb) {
-            add0 += p.temb[(size_t)n_img * p.temb_stride + col];
-            add1 += p.temb[(size_t)n_img * p.temb_stride + col + 1];
-        }
+        // per-channel addend: the conv bias, or (bias + time projection) pre-summed by the temb kernel
+        const float* addp = p.temb ? p.temb + (size_t)n_img * p.temb_stride : p.bias;
+        const float add0 = addp[col], add1 = addp[col + 1];
         float s = 0.f, ss = 0.f;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)

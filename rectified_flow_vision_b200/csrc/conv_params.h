@@ -7,7 +7,8 @@ namespace rfv {
 
 // out[n,ho,wo,co] = sum_{tap,c} A0[n, ho*stride+dy, wo*stride+dx, c] * W[co, tap*C0 + c]          (segment 0: ks x ks)
 //                 + sum_c  S1[n,ho,wo,c] * W[co, K0 + c]                                          (segment 1: 1x1 shortcut)
-//                 + bias[co] + temb[n*temb_stride + co] + resid[n,ho,wo,co]
+//                 + (temb ? temb[n*temb_stride + co] : bias[co]) + resid[n,ho,wo,co]
+//                   (when a time projection is present the conv bias is already folded into it)
 // All activations NHWC bf16.  Segment 1 may read a virtual channel-concat of two tensors (s1a | s1b).
 // `ups`: segment 0 input is nearest-upsampled x2 on the fly (logical input = 2*H0 x 2*W0).
 // GroupNorm partial statistics of the fp32 result are accumulated per (n, 8*k-channel slab):

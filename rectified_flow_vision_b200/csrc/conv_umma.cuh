@@ -1,13 +1,16 @@
 // Implicit-GEMM convolution on the 5th-gen tensor cores: TMA (tiled, zero-filled halo) -> 128B-swizzled shared
 // memory -> tcgen05.mma with fp32 accumulators in TMEM -> tcgen05.ld epilogue.  Persistent, warp-specialised:
 //   warp 0  TMA producer (one lane)      warp 1  MMA issuer (one lane)      warp 2  TMEM allocator
-//   warps 4-7  epilogue (one TMEM lane = one output pixel per thread)
+//   warps 4-11 epilogue (one TMEM lane = one output pixel per thread; two warps per lane quadrant split the columns)
 // GEMM view: M = 128 output pixels (a bn x bh x bw box of the NHWC tensor), N = BN output channels,
 // K = taps x C_in walked in chunks of 64 channels (one 128-byte swizzle row per pixel).  The im2col gather is done
 // by the TMA unit itself: for tap (dy,dx) the same 4-D box is fetched at (w0+dx-1, h0+dy-1); out-of-bounds
 // coordinates are zero-filled, which is exactly the conv's zero padding.  Stride-2 convs fetch from four
 // parity views of the input (one tensor map each).  A second K segment (1x1 shortcut over a virtual concat of up
 // to two tensors) accumulates into the same TMEM tile, so a ResidualBlock's conv2 + shortcut is one kernel.
+// Nearest-x2 upsample + 3x3 conv (models/unet.py:215-218) is never materialised: it is evaluated as four sub-pixel
+// phases, out[2i+py, 2j+px] = sum_{a,b in {0,1}} W'[py,px][a,b] . in[i+a+py-1, j+b+px-1], with the 3x3 taps that
+// alias onto the same input pixel pre-summed at weight-pack time (2.25x fewer MACs than the literal formulation).
 // Replaces nn.Conv2d call sites models/unet.py:38,41,51,76,77,185 (see SURVEY §2.4 for the shapes).
 #pragma once
 #include <cuda.h>
@@ -22,11 +25,13 @@ struct UmmaGeom {
     int tiles_w, tiles_h;     // boxes per image along W and H (1,1 when a box covers whole images)
     int m_tiles, n_tiles;
     int cch0, cch1a, cch1b;   // 64-channel chunks per tap of segment 0 / per source of segment 1
-    int taps;                 // 9 or 1
+    int taps;                 // 9, 1, or 4 (sub-pixel phases of a nearest-x2-upsample + 3x3 conv)
     int stride2;              // 1: segment 0 reads the four parity maps
+    int ups;                  // 1: output is 2x the input; tiles enumerate (pixel box, phase py/px, channel tile)
 };
 
 constexpr int UMMA_BM = 128;
+constexpr int UMMA_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int UMMA_A_BYTES = UMMA_BM * 128;  // 128 pixels x 64 bf16
 
 template <int BN>
@@ -39,7 +44,7 @@ struct UmmaCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                  const __grid_constant__ CUtensorMap mapW, const ConvParams p, const UmmaGeom g) {
@@ -66,7 +71,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 128);
+            mbar_init(&tempty_bar[s], UMMA_THREADS - 128);
         }
         mbar_fence_init();
     }
@@ -78,7 +83,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
     const int nkb0 = g.taps * g.cch0;
     const int nkb = nkb0 + g.cch1a + g.cch1b;
-    const int total_tiles = g.m_tiles * g.n_tiles;
+    const int phases = g.ups ? 4 : 1;
+    const int total_tiles = g.m_tiles * g.n_tiles * phases;
     const int box_shift = g.bw_shift + g.bh_shift;        // log2 pixels per image inside a box
     const int tiles_per_img = g.tiles_w * g.tiles_h;
 
@@ -87,7 +93,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             // ===================== TMA producer =====================
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+                const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
+                const int mt = rest / phases, sp = rest - mt * phases;  // sp: sub-pixel phase of an upsample conv
+                const int py = sp >> 1, px = sp & 1;
                 int n0, h0, w0;
                 if (box_shift >= 7) {
                     n0 = mt / tiles_per_img;
@@ -108,6 +116,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         const int tap = kb / g.cch0, cc = kb - tap * g.cch0;
                         int dy = 0, dx = 0;
                         if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; dy -= 1; dx -= 1; }
+                        else if (g.taps == 4) { dy = (tap >> 1) + py - 1; dx = (tap & 1) + px - 1; }
                         if (!g.stride2) {
                             tma_load_4d(sa, &mapA0, &full_bar[stage], cc * 64, w0 + dx, h0 + dy, n0);
                         } else {
@@ -122,7 +131,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         if (k1 < g.cch1a) tma_load_4d(sa, &mapA1, &full_bar[stage], k1 * 64, w0, h0, n0);
                         else tma_load_4d(sa, &mapA2, &full_bar[stage], (k1 - g.cch1a) * 64, w0, h0, n0);
                     }
-                    tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, nt * BN);
+                    tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, sp * p.Cout + nt * BN);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -155,12 +164,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;                 // TMEM lane quadrant
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access (warp id mod 4)
+        const int half = (warp - 4) >> 2;       // which interleaved half of the 32-column chunks this warp drains
         const int r = q * 32 + lane;            // row of the tile = output pixel
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
+            const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
+            const int mt = rest / phases, sp = rest - mt * phases;
             int n, h, w;
             if (box_shift >= 7) {
                 n = mt / tiles_per_img;
@@ -173,35 +184,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 w = r & ((1 << g.bw_shift) - 1);
             }
             const bool valid = n < p.B;
+            if (g.ups) { h = 2 * h + (sp >> 1); w = 2 * w + (sp & 1); }
             const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            for (int ch = half; ch < BN / 32; ch += 2) {
                 uint32_t acc[32];
                 tmem_ld32(taddr + ch * 32, acc);
                 tmem_ld_wait();
-                if (ch == BN / 32 - 1) {  // accumulator fully drained into registers: hand the TMEM stage back
+                if (ch + 2 >= BN / 32) {  // this thread's last chunk is in registers: hand its share of the TMEM stage back
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[as]);
                 }
                 const int c0 = nt * BN + ch * 32;
                 float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + c0 + i);
-                    v[i] = __uint_as_float(acc[i]) + b4.x;
-                    v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
-                    v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
-                    v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
-                }
-                if (p.temb && valid) {
-                    const float* te = p.temb + (size_t)n * p.temb_stride + c0;
+                {   // per-channel addend: the conv bias, or (bias + time projection) pre-summed by the temb kernel
+                    const float* add = p.temb ? p.temb + (size_t)(valid ? n : 0) * p.temb_stride + c0 : p.bias + c0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(te + i);
-                        v[i] += t4.x; v[i + 1] += t4.y; v[i + 2] += t4.z; v[i + 3] += t4.w;
+                        const float4 b4 = *reinterpret_cast<const float4*>(add + i);
+                        v[i] = __uint_as_float(acc[i]) + b4.x;
+                        v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
+                        v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
+                        v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
                     }
                 }
                 if (p.resid && valid) {
@@ -221,20 +228,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 }
                 if (p.stats) {
                     // a warp's 32 rows always lie inside one image (Ho*Wo % 32 == 0)
-                    const int n_w = __shfl_sync(0xffffffffu, n, 0);
-                    const bool v_w = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+                    // 8 partial sums per lane (4 slabs x {sum, sum of squares}) -> transposing butterfly: 9 shuffles,
+                    // after which lane L (L % 4 == 0) holds the warp total of value (L >> 2)
+                    float t8[8];
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
                         float s = 0.f, ss = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float x = v[sl * 8 + j]; s += x; ss += x * x; }
-                        s = warp_sum(s);
-                        ss = warp_sum(ss);
-                        if (lane == 0 && v_w) {
-                            float* dst = p.stats + ((size_t)n_w * (p.Cout >> p.slab_shift) + ((c0 + sl * 8) >> p.slab_shift)) * 2;
-                            atomicAdd(dst, s);
-                            atomicAdd(dst + 1, ss);
-                        }
+                        for (int j = 0; j < 8; ++j) { const float x = valid ? v[sl * 8 + j] : 0.f; s += x; ss += x * x; }
+                        t8[sl * 2] = s;
+                        t8[sl * 2 + 1] = ss;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float send = (lane & 16) ? t8[i] : t8[i + 4], keep = (lane & 16) ? t8[i + 4] : t8[i];
+                        t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = (lane & 8) ? t8[i] : t8[i + 2], keep = (lane & 8) ? t8[i + 2] : t8[i];
+                        t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    {
+                        const float send = (lane & 4) ? t8[0] : t8[1], keep = (lane & 4) ? t8[1] : t8[0];
+                        t8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    t8[0] += __shfl_xor_sync(0xffffffffu, t8[0], 2);
+                    t8[0] += __shfl_xor_sync(0xffffffffu, t8[0], 1);
+                    const int n_w = __shfl_sync(0xffffffffu, n, 0);
+                    const bool v_w = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+                    if ((lane & 3) == 0 && v_w) {
+                        const int idx = lane >> 2;  // value index: slab = idx >> 1, {sum, sumsq} = idx & 1
+                        float* dst = p.stats + ((size_t)n_w * (p.Cout >> p.slab_shift) + ((c0 + (idx >> 1) * 8) >> p.slab_shift)) * 2;
+                        atomicAdd(dst + (idx & 1), t8[0]);
                     }
                 }
             }

@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        bf16* __restrict__ out, int Ca, int Cb, int HW, int slab_shift,
                                                        int apply_silu, int pix_per_block, float eps) {
+    // blockDim.x is a multiple of C/8, so every thread owns ONE 8-channel vector position for the whole block and
+    // keeps its scale/shift in registers; the streaming loop is then load -> 8 FMAs (+SiLU) -> store.
     extern __shared__ float sm[];
     const int C = Ca + Cb;
     float* scale = sm;       // [C]
@@ -189,24 +191,41 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
         shift[c] = beta[c] - gmean[g] * sc;
     }
     __syncthreads();
-    const int vec_per_pix = C >> 3, va = Ca >> 3;
+    const int vpp = C >> 3;                       // 16-byte vectors per pixel
+    const int cv = threadIdx.x % vpp;             // this thread's vector position (fixed)
+    const int pl = threadIdx.x / vpp;             // pixel lane
+    const int pstride = blockDim.x / vpp;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[cv * 8 + j]; sh[j] = shift[cv * 8 + j]; }
+    const bool from_a = cv * 8 < Ca;
+    const bf16* src = from_a ? xa + cv * 8 : xb + (cv * 8 - Ca);
+    const int cs = from_a ? Ca : Cb;
     const int p0 = blockIdx.x * pix_per_block;
     const int np = min(pix_per_block, HW - p0);
-    const int total = np * vec_per_pix;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int pp = i / vec_per_pix, cv = i - pp * vec_per_pix;
-        const size_t pix = (size_t)n * HW + p0 + pp;
-        const uint4 q = (cv < va) ? *reinterpret_cast<const uint4*>(xa + pix * Ca + cv * 8)
-                                  : *reinterpret_cast<const uint4*>(xb + pix * Cb + (cv - va) * 8);
-        float f[8];
-        unpack8(q, f);
-        const int c = cv * 8;
+    const size_t base = (size_t)n * HW + p0;
+    constexpr int U = 4;
+    for (int pp = pl; pp < np; pp += U * pstride) {
+        uint4 q[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float y = f[j] * scale[c + j] + shift[c + j];
-            f[j] = apply_silu ? silu_f(y) : y;
+        for (int u = 0; u < U; ++u) {
+            const int px = pp + u * pstride;
+            if (px < np) q[u] = *reinterpret_cast<const uint4*>(src + (base + px) * cs);
         }
-        *reinterpret_cast<uint4*>(out + pix * C + c) = pack8(f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int px = pp + u * pstride;
+            if (px < np) {
+                float f[8];
+                unpack8(q[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float y = fmaf(f[j], sc[j], sh[j]);
+                    f[j] = apply_silu ? silu_f(y) : y;
+                }
+                *reinterpret_cast<uint4*>(out + (base + px) * C + cv * 8) = pack8(f);
+            }
+        }
     }
 }
 
@@ -307,6 +326,26 @@ __global__ void unpack_conv_weight_kernel(const bf16* __restrict__ src, float* _
         const int r = (int)(idx - (size_t)o * I * KK);
         const int i = r / KK, tap = r - i * KK;
         dst[idx] = __bfloat162float(src[(size_t)o * Ktot + k_off + tap * I + i]);
+    }
+}
+// Nearest-x2 upsample folded into a 3x3 conv: per output phase (py,px) a 2x2 kernel whose taps are sums of the 3x3
+// taps that land on the same input pixel.  dst[((py*2+px)*O + o)][(a*2+b)*I + i], bf16, sums formed in fp32.
+__global__ void pack_upsample_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
+    const size_t total = (size_t)16 * O * I;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % I);
+        const int tap = (int)((idx / I) % 4);
+        const int o = (int)((idx / ((size_t)4 * I)) % O);
+        const int phase = (int)(idx / ((size_t)4 * I * O));
+        const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+        // rows of the 3x3 kernel that alias onto input row i+a+py-1:  (py,a): (0,0)->{0} (0,1)->{1,2} (1,0)->{0,1} (1,1)->{2}
+        const int ky0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int kx0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        const float* w = src + ((size_t)o * I + i) * 9;
+        float acc = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
+        dst[idx] = __float2bfloat16_rn(acc);
     }
 }
 __global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {

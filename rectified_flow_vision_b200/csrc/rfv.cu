@@ -102,6 +102,7 @@ struct Op {
 struct ConvLayer {
     std::string name;
     int C0 = 0, Cout = 0, ks = 3, stride = 1, ups = 0, C1a = 0, C1b = 0, K0 = 0, Ktot = 0;
+    bool subpixel = false;  // ups layer packed as 4 phases x (2x2 taps): w is [4*Cout][4*C0]
     bf16* w = nullptr;
     float* bias = nullptr;  // fused (conv bias + shortcut bias)
 };
@@ -215,7 +216,9 @@ struct rfv_engine {
         auto L = std::make_unique<ConvLayer>();
         L->name = name; L->C0 = C0; L->Cout = Cout; L->ks = ks; L->stride = stride; L->ups = ups;
         L->C1a = C1a; L->C1b = C1b; L->K0 = ks * ks * C0; L->Ktot = L->K0 + C1a + C1b;
-        RFV_TRY(dalloc(&L->w, (size_t)Cout * L->Ktot));
+        L->subpixel = ups && use_umma && C0 % 64 == 0 && Cout % 64 == 0;
+        if (L->subpixel) { L->K0 = 4 * C0; L->Ktot = 4 * C0; }
+        RFV_TRY(dalloc(&L->w, (size_t)Cout * L->Ktot * (L->subpixel ? 4 : 1)));
         RFV_TRY(dalloc(&L->bias, (size_t)Cout));
         int iw, ib, isw = -1, isb = -1;
         RFV_TRY(add_param(name + ".weight", (int64_t)Cout * C0 * ks * ks, &iw));
@@ -227,13 +230,15 @@ struct rfv_engine {
             RFV_TRY(add_param(sc_name + ".bias", Cout, &isb));
         }
         params[iw].repack = [this, l, iw](cudaStream_t s) {
-            pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
+            if (l->subpixel) pack_upsample_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0);
+            else pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
             return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "pack launch failed");
         };
-        params[iw].readback = [this, l](float* dst, cudaStream_t s) {
-            unpack_conv_weight_kernel<<<256, 256, 0, s>>>(l->w, dst, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
-            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "unpack launch failed");
-        };
+        if (!L->subpixel)  // (the pre-summed sub-pixel taps cannot be un-summed: readback returns the fp32 upload)
+            params[iw].readback = [this, l](float* dst, cudaStream_t s) {
+                unpack_conv_weight_kernel<<<256, 256, 0, s>>>(l->w, dst, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
+                return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "unpack launch failed");
+            };
         auto fuse_bias = [this, l, ib, isb](cudaStream_t s) {
             add_vec_kernel<<<(l->Cout + 255) / 256, 256, 0, s>>>(pf(ib), isb >= 0 ? pf(isb) : nullptr, l->bias, l->Cout);
             return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "bias launch failed");
@@ -303,22 +308,26 @@ struct rfv_engine {
         p.ks = L->ks; p.stride = L->stride; p.ups = L->ups;
         p.C1a = L->C1a; p.C1b = L->C1b; p.K0 = L->K0; p.Ktot = L->Ktot;
         p.slab_shift = slab_shift;
-        const double fl = 2.0 * (double)L->Ktot * L->Cout * out->H * out->W;
+        const double fl = 2.0 * ((double)L->ks * L->ks * L->C0 + L->C1a + L->C1b) * L->Cout * out->H * out->W;  // algorithmic
         const int HoWo = out->H * out->W;
         if (HoWo % 32 != 0) return fail(RFV_ERR_INVALID, "conv %s: Ho*Wo=%d must be a multiple of 32", L->name.c_str(), HoWo);
 
-        const bool pow2 = is_pow2(out->W) && is_pow2(out->H);
-        const bool umma_ok = use_umma && pow2 && !L->ups && L->C0 % 64 == 0 && L->C1a % 64 == 0 && L->C1b % 64 == 0 &&
-                             L->Cout % 64 == 0 && HoWo >= 64 && out->W >= 8 && (L->stride == 1 || sc.empty());
+        // tile geometry lives on the grid the GEMM rows enumerate: the output pixels, or the INPUT pixels of an
+        // upsample conv (each input-resolution box yields four output phases)
+        const int gW = L->ups ? in0->W : out->W, gH = L->ups ? in0->H : out->H;
+        const bool pow2 = is_pow2(gW) && is_pow2(gH);
+        const bool umma_ok = use_umma && pow2 && (!L->ups || L->subpixel) && L->C0 % 64 == 0 && L->C1a % 64 == 0 &&
+                             L->C1b % 64 == 0 && L->Cout % 64 == 0 && gH * gW >= 64 && gW >= 8 && (L->stride == 1 || sc.empty());
+        if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
         if (umma_ok) {
             struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
-            const int bw = std::min(out->W, 128), bh = std::min(out->H, 128 / bw), bn = 128 / (bw * bh);
+            const int bw = std::min(gW, 128), bh = std::min(gH, 128 / bw), bn = 128 / (bw * bh);
             g.bw_shift = ilog2(bw); g.bh_shift = ilog2(bh);
-            g.tiles_w = out->W / bw; g.tiles_h = out->H / bh;
+            g.tiles_w = gW / bw; g.tiles_h = gH / bh;
             g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
-            g.taps = L->ks * L->ks; g.stride2 = (L->stride == 2);
+            g.taps = L->subpixel ? 4 : L->ks * L->ks; g.stride2 = (L->stride == 2); g.ups = L->subpixel ? 1 : 0;
             const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
             bd->BN = BN;
             g.n_tiles = L->Cout / BN;
@@ -342,26 +351,27 @@ struct rfv_engine {
                         RFV_TRY(make_map4(mp[ph * 2 + pw], in0->p + ((size_t)ph * Wi + pw) * C, C, Wi / 2, Hi / 2, capN,
                                           (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
             }
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN));
             const int sms = num_sms;
             const int sumC_ = sumC;
-            push("conv_umma", "conv:" + L->name, fl, [p, bd, HoWo, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+            const int gHW = gH * gW;
+            push("conv_umma", "conv:" + L->name, fl, [p, bd, gHW, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
                 ConvParams q = p;
                 q.B = rc.B;
                 q.temb_stride = rc.t ? sumC_ : 0;
                 UmmaGeom g = bd->g;
-                g.m_tiles = (int)(((size_t)rc.B * HoWo + 127) / 128);
-                const int total = g.m_tiles * g.n_tiles;
+                g.m_tiles = (int)(((size_t)rc.B * gHW + 127) / 128);
+                const int total = g.m_tiles * g.n_tiles * (g.ups ? 4 : 1);
                 const int grid = std::min(total, sms);
                 switch (bd->BN) {
                     case 256:
-                        conv_umma_kernel<256><<<grid, 256, UmmaCfg<256>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        conv_umma_kernel<256><<<grid, UMMA_THREADS, UmmaCfg<256>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                         break;
                     case 128:
-                        conv_umma_kernel<128><<<grid, 256, UmmaCfg<128>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        conv_umma_kernel<128><<<grid, UMMA_THREADS, UmmaCfg<128>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                         break;
                     default:
-                        conv_umma_kernel<64><<<grid, 256, UmmaCfg<64>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        conv_umma_kernel<64><<<grid, UMMA_THREADS, UmmaCfg<64>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                 }
                 return cudaGetLastError();
             });
@@ -398,12 +408,15 @@ struct rfv_engine {
         const float *gam = pf(ig), *bet = pf(ib);
         const int ss = slab_shift;
         if ((C / 8) % (1 << ss) != 0 || Ca % (1 << ss) != 0) return fail(RFV_ERR_INVALID, "gn %s: group/slab mismatch", name.c_str());
-        // ~32 KB of bf16 per block
-        int ppb = std::max(1, 16384 / C);
+        // ~128 KB of bf16 per block (amortises the per-block scale/shift prologue); threads = multiple of C/8
+        int ppb = std::max(1, 65536 / C);
         ppb = std::min(ppb, HW);
+        const int vpp = C / 8;
+        if (vpp > 256) return fail(RFV_ERR_INVALID, "gn %s: more than 2048 channels unsupported", name.c_str());
+        const int threads = (256 / vpp) * vpp;
         push("gn_apply", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             dim3 grid((HW + ppb - 1) / ppb, rc.B);
-            gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb, 1e-5f);
+            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb, 1e-5f);
             return cudaGetLastError();
         });
         return 0;
@@ -430,10 +443,17 @@ struct rfv_engine {
             cudaError_t e = cudaMemcpyAsync(wcat + (size_t)off * td, pf(iw), (size_t)Cout * td * sizeof(float), cudaMemcpyDeviceToDevice, s);
             return e == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "wcat copy failed");
         };
-        params[ib].repack = [this, ib, off, Cout](cudaStream_t s) {
-            cudaError_t e = cudaMemcpyAsync(bcat + off, pf(ib), (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, s);
-            return e == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "bcat copy failed");
+        // bcat rows = time_mlp bias + conv1 bias: the conv epilogue then adds ONE vector per channel
+        const int icb = param_index["velocity_net." + name + ".conv1.bias"];
+        auto fuse = [this, ib, icb, off, Cout](cudaStream_t s) {
+            add_vec_kernel<<<(Cout + 255) / 256, 256, 0, s>>>(pf(ib), pf(icb), bcat + off, Cout);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "bcat fuse failed");
         };
+        params[ib].repack = fuse;
+        {
+            auto prev = params[icb].repack;
+            params[icb].repack = [prev, fuse](cudaStream_t s) { int rc = prev ? prev(s) : 0; return rc ? rc : fuse(s); };
+        }
         RFV_TRY(conv_op(c1, a1, {}, nullptr, h, off, true));
         release(a1);
         RFV_TRY(new_act(&a2, Cout, H, W, false));

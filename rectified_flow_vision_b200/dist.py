@@ -1,0 +1,84 @@
+"""Batch-dimension sharding of sampling / reflow pair generation across the GPUs of one box.
+
+The reference has no multi-device path.  Every image is an independent ODE solve, so the work is
+partitioned along the batch: rank r of W integrates a contiguous slice of the host-seeded noise; there is NO
+communication while integrating and exactly one collective at the end (an all-gather of the results over
+NCCL / NVLink), mirroring ``generate_reflow_pairs`` (models/rectified_flow.py:127-174) which returns the full
+pair tensors on the host.  One process per GPU (torchrun); weights are replicated (identical seed / checkpoint).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced row range of rank `rank`: the first n % world ranks get one extra row."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def seeded_noise(num: int, channels: int, size: int, seed: int) -> torch.Tensor:
+    """The whole job's noise, identical on every rank (CPU generator, fixed seed) -- the north star's
+    'noise comes from the host with a fixed seed, so inputs are identical to the reference'."""
+    return torch.randn(num, channels, size, size, generator=torch.Generator().manual_seed(seed))
+
+
+def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, gather: bool = True,
+                group=None) -> torch.Tensor:
+    """Apply `fn` to this rank's slice of `rows` (a CPU tensor identical on all ranks); optionally all-gather the
+    per-rank results back into row order.  `fn` maps a CPU tensor [k, ...] to a CPU tensor [k, ...]."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return fn(rows)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(rows.shape[0], rank, world)
+    local = fn(rows[lo:hi])
+    if not gather:
+        return local
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    width = -(-rows.shape[0] // world)  # equal-sized slots for the collective; short shards are padded
+    slot = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    slot[: hi - lo].copy_(local, non_blocking=True)
+    gathered = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, slot, group=group)
+    gathered = gathered.cpu()
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(rows.shape[0], r, world)
+        parts.append(gathered[r * width: r * width + (b - a)])
+    return torch.cat(parts, dim=0)
+
+
+def generate_reflow_pairs_sharded(teacher_model, num_pairs: int, num_steps: int = 100,
+                                  noise: Optional[torch.Tensor] = None, seed: int = 42, gather: bool = True,
+                                  group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Multi-GPU ``generate_reflow_pairs``: returns (x0, x1) as CPU fp32 tensors.  With gather=True both hold all
+    `num_pairs` rows on every rank; with gather=False they hold this rank's rows only."""
+    teacher_model.eval()
+    c, s = teacher_model.in_channels, teacher_model.image_size
+    if noise is None:
+        noise = seeded_noise(num_pairs, c, s, seed)
+    noise = noise.to(torch.float32).cpu().contiguous()
+
+    def integrate(x0: torch.Tensor) -> torch.Tensor:
+        if x0.shape[0] == 0:
+            return x0.clone()
+        x0 = x0.contiguous()
+        if torch.cuda.is_available() and not x0.is_pinned():
+            x0 = x0.pin_memory()
+        return teacher_model._engine(s).euler_sample_host(x0, num_steps)
+
+    x1 = sharded_map(integrate, noise, gather=gather, group=group)
+    if gather or not (dist.is_available() and dist.is_initialized()):
+        return noise, x1
+    lo, hi = shard_bounds(num_pairs, dist.get_rank(group), dist.get_world_size(group))
+    return noise[lo:hi], x1
+
+
+def sample_sharded(model, noise: torch.Tensor, num_steps: int, gather: bool = True, group=None) -> torch.Tensor:
+    """Multi-GPU ``BaseFlowModel.sample`` on host noise (same partition as above)."""
+    return generate_reflow_pairs_sharded(model, noise.shape[0], num_steps, noise=noise, gather=gather, group=group)[1]

@@ -151,10 +151,10 @@ class UNet(_Node):
         return eng
 
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        if self.training and torch.is_grad_enabled():
+        if self.training:
             raise NotImplementedError(
-                "training-mode forward with autograd is not part of the native path yet (SURVEY §8 a15); "
-                "call under torch.no_grad() / eval().")
+                "training-mode forward (dropout + autograd) is not part of the native path yet (SURVEY §8 a15) and "
+                "there is no PyTorch fallback; call model.eval() first.")
         if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape [B,{self.in_channels},S,S], got {tuple(x.shape)}")
         if t.dim() != 1 or t.shape[0] != x.shape[0]:
