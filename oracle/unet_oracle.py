@@ -263,8 +263,8 @@ def unet_forward(P: Dict[str, np.ndarray], x: np.ndarray, t: np.ndarray, spec: O
 
     a = pol.act(silu(group_norm(h, P[pre + "output_conv.0.weight"], P[pre + "output_conv.0.bias"],
                                 stats_from=h_full)))
-    # the 64->3 output conv runs on CUDA cores with fp32 weights and writes fp32
-    return conv2d(a, P[pre + "output_conv.2.weight"], P[pre + "output_conv.2.bias"], 1, 1)
+    # the 64->3 output conv runs on tensor cores (bf16 weights, fp32 accumulate) and writes fp32
+    return conv2d(a, pol.w(P[pre + "output_conv.2.weight"]), P[pre + "output_conv.2.bias"], 1, 1)
 
 
 # ----------------------------------------------------------------------------------------------------------

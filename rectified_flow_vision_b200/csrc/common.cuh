@@ -37,6 +37,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Transposing butterfly: 8 values per lane -> after 9 shuffles lane L holds in t[0] the warp-wide sum of value
+// ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1)  (all four lanes of a quad hold the same total).
+__device__ __forceinline__ void warp_reduce8(float* t, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = (lane & 16) ? t[i] : t[i + 4], keep = (lane & 16) ? t[i + 4] : t[i];
+        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = (lane & 8) ? t[i] : t[i + 2], keep = (lane & 8) ? t[i + 2] : t[i];
+        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = (lane & 4) ? t[0] : t[1], keep = (lane & 4) ? t[1] : t[0];
+        t[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------------------------------------------------

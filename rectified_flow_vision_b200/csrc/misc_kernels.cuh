@@ -77,64 +77,78 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Input conv 3x3, C_in small (3): fp32 NCHW in -> bf16 NHWC out (+ GroupNorm slab statistics).  models/unet.py:165,234
+// Input conv 3x3, C_in small (<= 4): fp32 NCHW in -> bf16 NHWC out (+ GroupNorm slab statistics).  models/unet.py:165,234
 // Optionally computes the flow-matching interpolation on the fly: x = (1-t) x0 + t x1   (models/base_flow.py:84).
-// Block = 64 consecutive pixels of one image x all C_out channels; 256 threads = 64 pixels x 4 channel phases.
+// One thread = one output pixel x all C_out channels: its 9*C_in inputs live in registers, weights are broadcast from
+// shared memory ([k][co] fp32, pre-transposed at upload time), output rows are written as contiguous 16-byte vectors.
 // ---------------------------------------------------------------------------------------------------------
+template <int CIN>
 __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict__ x, const float* __restrict__ x1,
-                                                         const float* __restrict__ tvec, const float* __restrict__ w,
+                                                         const float* __restrict__ tvec, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, bf16* __restrict__ out,
-                                                         float* __restrict__ stats, int Cin, int H, int W, int Cout,
-                                                         int slab_shift) {
+                                                         float* __restrict__ stats, int H, int W, int Cout, int slab_shift) {
+    constexpr int K = CIN * 9;
     extern __shared__ float sm[];
-    const int K = Cin * 9;
-    float* wsm = sm;                   // [K][Cout]
-    float* patch = sm + K * Cout;      // [64][K+1]
-    float* st = patch + 64 * (K + 1);  // [Cout/8][2]
+    float* wsm = sm;               // [K][Cout]
+    float* bsm = sm + K * Cout;    // [Cout]
+    float* st = bsm + Cout;        // [Cout/8][2]
     const int HW = H * W;
-    const int n = blockIdx.y, p0 = blockIdx.x * 64;
-    for (int i = threadIdx.x; i < K * Cout; i += 256) {  // w is OIHW: [co][ci][kh][kw] -> wsm[(ci*9+kh*3+kw)][co]
-        const int co = i / K, k = i - co * K;
-        wsm[k * Cout + co] = w[i];
-    }
+    const int n = blockIdx.y, pix = blockIdx.x * 256 + threadIdx.x;
+    for (int i = threadIdx.x; i < K * Cout; i += 256) wsm[i] = wt[i];
+    for (int i = threadIdx.x; i < Cout; i += 256) bsm[i] = bias[i];
     for (int i = threadIdx.x; i < (Cout / 8) * 2; i += 256) st[i] = 0.f;
+    const int h = pix / W, w = pix - h * W;
     const float tb = (x1 != nullptr) ? tvec[n] : 0.f;
-    for (int i = threadIdx.x; i < 64 * K; i += 256) {
-        const int k = i / 64, pp = i - k * 64;  // consecutive threads -> consecutive pixels (coalesced)
-        const int ci = k / 9, tap = k - ci * 9;
-        const int pix = p0 + pp;
-        const int h = pix / W + tap / 3 - 1, ww = pix % W + tap % 3 - 1;
-        float v = 0.f;
-        if (h >= 0 && h < H && ww >= 0 && ww < W) {
-            const size_t o = ((size_t)n * Cin + ci) * HW + (size_t)h * W + ww;
-            v = x[o];
-            if (x1 != nullptr) v = (1.0f - tb) * v + tb * x1[o];
-        }
-        patch[pp * (K + 1) + k] = v;
-    }
+    float in[K];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int hh = h + ky - 1, ww = w + kx - 1;
+                float v = 0.f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    const size_t o = ((size_t)n * CIN + ci) * HW + (size_t)hh * W + ww;
+                    v = x[o];
+                    if (x1 != nullptr) v = (1.0f - tb) * v + tb * x1[o];
+                }
+                in[ci * 9 + ky * 3 + kx] = v;
+            }
     __syncthreads();
-    const int pp = threadIdx.x >> 2, q = threadIdx.x & 3;
-    const float* pr = patch + pp * (K + 1);
-    for (int co = q * 8; co < Cout; co += 32) {
-        float acc[8];
+    const int lane = threadIdx.x & 31;
+    bf16* orow = out + ((size_t)n * HW + pix) * Cout;
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        float acc[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = bias[co + j];
+        for (int j = 0; j < 32; ++j) acc[j] = bsm[c0 + j];
+#pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float a = pr[k];
-            const float4 w0 = *reinterpret_cast<const float4*>(wsm + k * Cout + co);
-            const float4 w1 = *reinterpret_cast<const float4*>(wsm + k * Cout + co + 4);
-            acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
-            acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+            const float a = in[k];
+            const float4* wr = reinterpret_cast<const float4*>(wsm + k * Cout + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w4 = wr[j];
+                acc[4 * j] = fmaf(a, w4.x, acc[4 * j]);
+                acc[4 * j + 1] = fmaf(a, w4.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(a, w4.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(a, w4.w, acc[4 * j + 3]);
+            }
         }
-        *reinterpret_cast<uint4*>(out + ((size_t)n * HW + p0 + pp) * Cout + co) = pack8(acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + c0 + j * 8) = pack8(acc + j * 8);
         if (stats) {
-            float s = 0.f, ss = 0.f;
+            float t8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s += acc[j]; ss += acc[j] * acc[j]; }
-            // reduce over the 8 pixels of this warp that share q (lane bits 2..4)
+            for (int sl = 0; sl < 4; ++sl) {
+                float s = 0.f, ss = 0.f;
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-            if ((threadIdx.x & 31) < 4) { atomicAdd(&st[(co >> 3) * 2], s); atomicAdd(&st[(co >> 3) * 2 + 1], ss); }
+                for (int j = 0; j < 8; ++j) { const float v = acc[sl * 8 + j]; s += v; ss += v * v; }
+                t8[sl * 2] = s;
+                t8[sl * 2 + 1] = ss;
+            }
+            warp_reduce8(t8, lane);
+            if ((lane & 3) == 0) atomicAdd(&st[((c0 >> 3) + (lane >> 3)) * 2 + ((lane >> 2) & 1)], t8[0]);
         }
     }
     if (stats) {
@@ -145,6 +159,11 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
             atomicAdd(dst + 1, st[i * 2 + 1]);
         }
     }
+}
+// OIHW fp32 -> [ci*9+tap][co] fp32 (the layout input_conv_kernel stages into shared memory)
+__global__ void transpose_input_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < O * K) { const int o = i / K, k = i - o * K; dst[k * O + o] = src[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -230,77 +249,125 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Output conv 3x3, C -> C_out (3), fused with what follows it at the call site:
+// Output conv 3x3, C -> C_out (<= 4), fused with what follows it at the call site:
 //   mode 0  v = conv(a)                                      (UNet.forward result, models/unet.py:275)
 //   mode 1  x += dt * conv(a)   [+ snapshot into traj]       (Euler update, models/base_flow.py:170)
+//   mode 2  nothing is written (loss only)
 // and optionally accumulates sum((conv(a) - target)^2), target = x1 - x0, for the loss / straightness metrics
 // (models/rectified_flow.py:118,231).  a: NHWC bf16 (already GroupNorm+SiLU'd); x, v, x0, x1: NCHW fp32.
-// Block = 8 x 32 output pixels, halo tile of `a` staged in shared memory (pixel pitch padded by 16 B).
+// Tensor-core formulation: per 8x32-pixel tile the halo of `a` is staged in shared memory (cp.async, double
+// buffered across the tiles a persistent block walks); im2col is free -- each ldmatrix row address simply points at
+// the tap-shifted pixel of the halo tile.  GEMM per warp: M = 32 pixels (one tile row), N = 8 (C_out padded),
+// K = 9*C, mma.sync m16n8k16 with bf16 weights [tap][n][C].
 // ---------------------------------------------------------------------------------------------------------
 constexpr int OC_TH = 8, OC_TW = 32;
-__global__ void __launch_bounds__(256) output_conv_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) output_conv_kernel(const bf16* __restrict__ a, const bf16* __restrict__ wpk,
                                                           const float* __restrict__ bias, float* __restrict__ xv,
                                                           float* __restrict__ traj, const float* __restrict__ x0,
                                                           const float* __restrict__ x1, float* __restrict__ mse_acc,
-                                                          int C, int H, int W, int Cout, int mode, float dt) {
+                                                          int C, int H, int W, int Cout, int B, int mode, float dt) {
     extern __shared__ __align__(16) uint8_t smraw[];
-    const int pitch = C * 2 + 16;                                  // bytes per staged pixel
-    uint8_t* tile = smraw;                                         // [(TH+2)*(TW+2)][pitch]
-    float* wsm = reinterpret_cast<float*>(smraw + (OC_TH + 2) * (OC_TW + 2) * pitch);  // [Cout][9][C]
+    const int pitch = C * 2 + 16;                                  // bytes per staged pixel / weight row
+    const int tile_bytes = (OC_TH + 2) * (OC_TW + 2) * pitch;
+    uint8_t* tiles = smraw;                                        // 2 x [(TH+2)*(TW+2)][pitch]
+    uint8_t* wsm = smraw + 2 * tile_bytes;                         // [9][8][pitch]
     __shared__ float red[8];
-    const int n = blockIdx.z, h0 = blockIdx.y * OC_TH, w0 = blockIdx.x * OC_TW;
-    for (int i = threadIdx.x; i < Cout * 9 * C; i += 256) {  // OIHW [co][c][tap] -> wsm[co][tap][c]
-        const int co = i / (9 * C), r = i - co * 9 * C, c = r / 9, tap = r - c * 9;
-        wsm[(co * 9 + tap) * C + c] = w[i];
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tw = (W + OC_TW - 1) / OC_TW, th = (H + OC_TH - 1) / OC_TH;
+    const int ntiles = tw * th * B;
     const int vec = C >> 3;
-    for (int i = threadIdx.x; i < (OC_TH + 2) * (OC_TW + 2) * vec; i += 256) {
-        const int pp = i / vec, cv = i - pp * vec;
-        const int hh = h0 + pp / (OC_TW + 2) - 1, ww = w0 + pp % (OC_TW + 2) - 1;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-            q = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + hh) * W + ww) * C + cv * 8);
-        *reinterpret_cast<uint4*>(tile + pp * pitch + cv * 16) = q;
+    for (int i = tid; i < 9 * 8 * vec; i += 256) {  // packed weights [tap][8][C] bf16 -> padded rows
+        const int row = i / vec, cv = i - row * vec;
+        *reinterpret_cast<uint4*>(wsm + row * pitch + cv * 16) = *reinterpret_cast<const uint4*>(wpk + (size_t)row * C + cv * 8);
     }
-    __syncthreads();
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // Cout <= 4
-    for (int tap = 0; tap < 9; ++tap) {
-        const uint8_t* src = tile + ((ty + tap / 3) * (OC_TW + 2) + tx + tap % 3) * pitch;
-        for (int cv = 0; cv < vec; ++cv) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(src + cv * 16), f);
-            for (int co = 0; co < Cout; ++co) {
-                const float* wr = wsm + (co * 9 + tap) * C + cv * 8;
-                const float4 wa = *reinterpret_cast<const float4*>(wr), wb = *reinterpret_cast<const float4*>(wr + 4);
-                acc[co] += f[0] * wa.x + f[1] * wa.y + f[2] * wa.z + f[3] * wa.w + f[4] * wb.x + f[5] * wb.y + f[6] * wb.z + f[7] * wb.w;
-            }
+    auto stage_tile = [&](int tile, int buf) {
+        const int n = tile / (tw * th), r = tile - n * (tw * th);
+        const int h0 = (r / tw) * OC_TH, w0 = (r - (r / tw) * tw) * OC_TW;
+        uint8_t* dst = tiles + buf * tile_bytes;
+        for (int i = tid; i < (OC_TH + 2) * (OC_TW + 2) * vec; i += 256) {
+            const int pp = i / vec, cv = i - pp * vec;
+            const int hh = h0 + pp / (OC_TW + 2) - 1, ww = w0 + pp % (OC_TW + 2) - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const bf16* src = ok ? a + (((size_t)n * H + hh) * W + ww) * C + cv * 8 : a;
+            cp_async16(smem_u32(dst + pp * pitch + cv * 16), src, ok);
         }
-    }
-    const int h = h0 + ty, ww = w0 + tx;
+    };
     float sq = 0.f;
-    if (h < H && ww < W) {
-        for (int co = 0; co < Cout; ++co) {
-            const float val = acc[co] + bias[co];
-            const size_t o = (((size_t)n * Cout + co) * H + h) * W + ww;
-            if (mse_acc) { const float d = val - (x1[o] - x0[o]); sq += d * d; }
-            if (mode == 0) xv[o] = val;
-            else {
-                const float nx = xv[o] + val * dt;
-                xv[o] = nx;
-                if (traj) traj[o] = nx;
+    int buf = 0;
+    if ((int)blockIdx.x < ntiles) stage_tile(blockIdx.x, 0);
+    cp_async_commit();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int nxt = tile + gridDim.x;
+        if (nxt < ntiles) stage_tile(nxt, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint8_t* tb = tiles + buf * tile_bytes;
+        float acc[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            // A rows: pixel (warp + ky, m*16 + lane%16 + kx) of the halo tile; k half selected by lane/16
+            const uint8_t* arow = tb + ((warp + ky) * (OC_TW + 2) + (lane & 15) + kx) * pitch + (lane >> 4) * 16;
+            // B rows: weight row n = lane%8 of this tap; lanes 8-15 address the k+8 half (ldmatrix.x2 uses lanes 0-15)
+            const uint8_t* brow = wsm + (tap * 8 + (lane & 7)) * pitch + ((lane >> 3) & 1) * 16;
+            for (int kc = 0; kc < C / 16; ++kc) {
+                uint32_t b0, b1;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(smem_u32(brow + kc * 32)));
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    uint32_t af[4];
+                    ldmatrix_x4(smem_u32(arow + m * 16 * pitch + kc * 32), af[0], af[1], af[2], af[3]);
+                    mma_bf16_16816(acc[m], af, b0, b1);
+                }
             }
         }
+        // epilogue: thread holds (pixel g / g+8 of each m-tile) x (channels 2t, 2t+1)
+        const int n = tile / (tw * th), r = tile - n * (tw * th);
+        const int h = (r / tw) * OC_TH + warp, w0 = (r - (r / tw) * tw) * OC_TW;
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int co = tq * 2 + j, w = w0 + m * 16 + g + hh * 8;
+                    if (co < Cout && h < H && w < W) {
+                        const float val = acc[m][hh * 2 + j] + bias[co];
+                        const size_t o = (((size_t)n * Cout + co) * H + h) * W + w;
+                        if (mse_acc) { const float d = val - (x1[o] - x0[o]); sq += d * d; }
+                        if (mode == 0) xv[o] = val;
+                        else if (mode == 1) {
+                            const float nx = xv[o] + val * dt;
+                            xv[o] = nx;
+                            if (traj) traj[o] = nx;
+                        }
+                    }
+                }
+        __syncthreads();  // all warps done with this buffer before it is refilled two iterations later
     }
+    cp_async_wait<0>();
     if (mse_acc) {
         sq = warp_sum(sq);
-        if (tx == 0) red[ty] = sq;
+        if (lane == 0) red[warp] = sq;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             float s = 0.f;
             for (int i = 0; i < 8; ++i) s += red[i];
             atomicAdd(mse_acc, s);
         }
+    }
+}
+// OIHW fp32 [co][c][3][3] -> bf16 [tap][8][C] (rows co >= Cout are zero): the B operand of output_conv_kernel
+__global__ void pack_output_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * 8 * C) {
+        const int c = i % C, nrow = (i / C) % 8, tap = i / (8 * C);
+        dst[i] = __float2bfloat16_rn(nrow < Cout ? src[((size_t)nrow * C + c) * 9 + tap] : 0.f);
     }
 }
 

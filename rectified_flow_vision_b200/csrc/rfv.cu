@@ -532,16 +532,27 @@ int rfv_engine::build() {
         RFV_TRY(add_param("input_conv.weight", (int64_t)mc * cfg.in_channels * 9, &iw));
         RFV_TRY(add_param("input_conv.bias", mc, &ib));
         RFV_TRY(new_act(&h, mc, S, S, true));
-        const float *w = pf(iw), *b = pf(ib);
-        bf16* o = h->p;
-        float* st = h->stats;
         const int Cin = cfg.in_channels, ss = slab_shift;
         const int K = Cin * 9;
-        const size_t smem = ((size_t)K * mc + 64 * (K + 1) + (mc / 8) * 2) * sizeof(float);
-        if ((S * S) % 64 != 0) return fail(RFV_ERR_INVALID, "image_size^2 must be a multiple of 64");
+        float* wt = nullptr;  // [K][mc] fp32: the layout the kernel stages into shared memory
+        RFV_TRY(dalloc(&wt, (size_t)K * mc));
+        params[iw].repack = [this, iw, wt, K, mc](cudaStream_t s) {
+            transpose_input_weight_kernel<<<(K * mc + 255) / 256, 256, 0, s>>>(pf(iw), wt, mc, K);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "input weight transpose failed");
+        };
+        const float* b = pf(ib);
+        bf16* o = h->p;
+        float* st = h->stats;
+        const size_t smem = ((size_t)K * mc + mc + (mc / 8) * 2) * sizeof(float);
+        if ((S * S) % 256 != 0) return fail(RFV_ERR_INVALID, "image_size^2 must be a multiple of 256");
         push("input_conv", "conv:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-            dim3 grid(S * S / 64, rc.B);
-            input_conv_kernel<<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, w, b, o, st, Cin, S, S, mc, ss);
+            dim3 grid(S * S / 256, rc.B);
+            switch (Cin) {
+                case 1: input_conv_kernel<1><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
+                case 2: input_conv_kernel<2><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
+                case 3: input_conv_kernel<3><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
+                default: input_conv_kernel<4><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
+            }
             return cudaGetLastError();
         });
         named_acts["input_conv"] = h;
@@ -655,13 +666,23 @@ int rfv_engine::build() {
         RFV_TRY(add_param("output_conv.2.weight", (int64_t)Co * C * 9, &iw));
         RFV_TRY(add_param("output_conv.2.bias", Co, &ib));
         if (Co > 4) return fail(RFV_ERR_INVALID, "out_channels > 4 unsupported");
-        const float *w = pf(iw), *b = pf(ib);
+        bf16* wpk = nullptr;  // [9 taps][8 (C_out padded)][C] bf16: B operand of the mma.sync formulation
+        RFV_TRY(dalloc(&wpk, (size_t)9 * 8 * C));
+        params[iw].repack = [this, iw, wpk, Co, C](cudaStream_t s) {
+            pack_output_weight_kernel<<<(9 * 8 * C + 255) / 256, 256, 0, s>>>(pf(iw), wpk, Co, C);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "output weight pack failed");
+        };
+        const float* b = pf(ib);
         const bf16* ap = a->p;
-        const size_t smem = (size_t)(OC_TH + 2) * (OC_TW + 2) * (C * 2 + 16) + (size_t)Co * 9 * C * sizeof(float);
+        const int pitch = C * 2 + 16;
+        const size_t smem = (size_t)2 * (OC_TH + 2) * (OC_TW + 2) * pitch + (size_t)9 * 8 * pitch;
+        if (smem > 227 * 1024) return fail(RFV_ERR_INVALID, "output conv: %d channels do not fit the shared-memory tile", C);
         CU_CHECK(cudaFuncSetAttribute(output_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int sms = num_sms;
         push("output_conv", "conv:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-            dim3 grid((S + OC_TW - 1) / OC_TW, (S + OC_TH - 1) / OC_TH, rc.B);
-            output_conv_kernel<<<grid, 256, smem, s>>>(ap, w, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.mode, rc.dt);
+            const int ntiles = ((S + OC_TW - 1) / OC_TW) * ((S + OC_TH - 1) / OC_TH) * rc.B;
+            const int grid = std::min(ntiles, 2 * sms);
+            output_conv_kernel<<<grid, 256, smem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.B, rc.mode, rc.dt);
             return cudaGetLastError();
         });
         release(a);
