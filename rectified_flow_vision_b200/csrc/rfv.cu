@@ -143,6 +143,24 @@ struct rfv_engine {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_cmp = nullptr;
     cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{};
     cudaEvent_t ev_weights = nullptr;  // last parameter upload (made on the caller's stream)
+    cudaEvent_t ev_last = nullptr;     // end of the last enqueued call: the arena is shared, calls on different
+    cudaStream_t last_stream = nullptr;  // streams are chained through this event
+    bool have_last = false;
+
+    int enter(cudaStream_t s) {
+        if (have_last && s != last_stream) {
+            cudaError_t e = cudaStreamWaitEvent(s, ev_last, 0);
+            if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+        }
+        return 0;
+    }
+    int leave(cudaStream_t s) {
+        cudaError_t e = cudaEventRecord(ev_last, s);
+        if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+        last_stream = s;
+        have_last = true;
+        return 0;
+    }
 
     int64_t launches = 0;
     double flops_per_image = 0;
@@ -159,6 +177,7 @@ struct rfv_engine {
             if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (ev_weights) cudaEventDestroy(ev_weights);
+        if (ev_last) cudaEventDestroy(ev_last);
         if (s_h2d) cudaStreamDestroy(s_h2d);
         if (s_d2h) cudaStreamDestroy(s_d2h);
         if (s_cmp) cudaStreamDestroy(s_cmp);
@@ -760,6 +779,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
     {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -834,13 +854,14 @@ RFV_EXPORT int rfv_velocity(rfv_handle h, const float* x, const float* t, float*
     if (!h || !x || !t || !v || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
     if (h->cfg.in_channels != h->cfg.out_channels) return fail(RFV_ERR_INVALID, "in_channels != out_channels");
     const size_t ie = image_elems(h);
+    RFV_TRY(h->enter((cudaStream_t)stream));
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
         RunCtx rc;
         rc.B = (int)std::min<int64_t>(h->cap, batch - b0);
         rc.x = x + b0 * ie; rc.t = t + b0; rc.out = v + b0 * ie; rc.mode = 0;
         RFV_TRY(h->run_forward(rc, (cudaStream_t)stream));
     }
-    return 0;
+    return h->leave((cudaStream_t)stream);
 }
 
 static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj, int save_every, size_t traj_stride,
@@ -860,18 +881,20 @@ static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj
 RFV_EXPORT int rfv_euler_sample(rfv_handle h, float* x, int64_t batch, int num_steps, float* traj, int save_every, void* stream) {
     if (!h || !x || batch < 1 || num_steps < 1) return fail(RFV_ERR_INVALID, "bad argument");
     const size_t ie = image_elems(h);
+    RFV_TRY(h->enter((cudaStream_t)stream));
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
         const int B = (int)std::min<int64_t>(h->cap, batch - b0);
         RFV_TRY(euler_chunk(h, x + b0 * ie, B, num_steps, traj ? traj + b0 * ie : nullptr, save_every, (size_t)batch * ie, nullptr,
                             nullptr, nullptr, (cudaStream_t)stream));
     }
-    return 0;
+    return h->leave((cudaStream_t)stream);
 }
 
 RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, float* out_host, int64_t n, int num_steps) {
     if (!h || !noise_host || !out_host || n < 1 || num_steps < 1) return fail(RFV_ERR_INVALID, "bad argument");
     const size_t ie = image_elems(h);
     CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_weights, 0));  // uploads were enqueued on the caller's stream
+    RFV_TRY(h->enter(h->s_cmp));
     int64_t idx = 0;
     for (int64_t b0 = 0; b0 < n; b0 += h->cap, ++idx) {
         const int B = (int)std::min<int64_t>(h->cap, n - b0);
@@ -889,13 +912,14 @@ RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, floa
     }
     CU_CHECK(cudaStreamSynchronize(h->s_d2h));
     CU_CHECK(cudaStreamSynchronize(h->s_cmp));
-    return 0;
+    return h->leave(h->s_cmp);
 }
 
 RFV_EXPORT int rfv_straightness(rfv_handle h, const float* x0, const float* x1, int64_t batch, int num_points, float* dev_out, void* stream) {
     if (!h || !x0 || !x1 || !dev_out || batch < 1 || num_points < 1) return fail(RFV_ERR_INVALID, "bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t ie = image_elems(h);
+    RFV_TRY(h->enter(s));
     CU_CHECK(cudaMemsetAsync(dev_out, 0, (size_t)num_points * sizeof(float), s));
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
         const int B = (int)std::min<int64_t>(h->cap, batch - b0);
@@ -904,13 +928,14 @@ RFV_EXPORT int rfv_straightness(rfv_handle h, const float* x0, const float* x1, 
     }
     scale_kernel<<<(num_points + 255) / 256, 256, 0, s>>>(dev_out, num_points, 1.0f / (float)((double)batch * ie));
     CU_CHECK(cudaGetLastError());
-    return 0;
+    return h->leave(s);
 }
 
 RFV_EXPORT int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch, float* loss_out, void* stream) {
     if (!h || !x0 || !x1 || !t || !loss_out || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t ie = image_elems(h);
+    RFV_TRY(h->enter(s));
     CU_CHECK(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
         RunCtx rc;
@@ -921,7 +946,7 @@ RFV_EXPORT int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const
     }
     scale_kernel<<<1, 32, 0, s>>>(loss_out, 1, 1.0f / (float)((double)batch * ie));
     CU_CHECK(cudaGetLastError());
-    return 0;
+    return h->leave(s);
 }
 
 RFV_EXPORT int64_t rfv_launch_count(rfv_handle h, int reset) {
