@@ -55,6 +55,10 @@ typedef struct {
 #define RFV_FLAG_NO_UMMA   1   /* force the mma.sync implicit-GEMM kernel everywhere (debug / A-B testing) */
 #define RFV_FLAG_NO_GRAPH  2   /* launch kernels directly instead of replaying a captured CUDA graph */
 #define RFV_FLAG_KEEP_ACTS 4   /* never recycle activation buffers, so rfv_debug_activation can read any layer */
+#define RFV_FLAG_NO_HALO   8   /* do not use the halo-reuse tcgen05 kernel (A/B testing against the per-tap kernel) */
+#define RFV_FLAG_BASEOFF   16  /* halo kernel: also set the UMMA descriptor base-offset field to (addr>>7)&7.  Measured on
+                                  B200: WRONG results -- the 128B swizzle is applied on absolute smem address bits, so
+                                  shifted (128-byte aligned) start addresses need base offset 0.  Kept as an experiment. */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int rfv_abi_version(void);

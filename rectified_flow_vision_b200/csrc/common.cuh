@@ -58,6 +58,18 @@ __device__ __forceinline__ void warp_reduce8(float* t, int lane) {
     t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
 }
 
+// One lane of a fully converged warp (elect.sync): role loops stay warp-uniform, so ptxas keeps the uniform-datapath
+// instructions (UTCHMMA / UTMALDG / UTCBAR) free of the ELECT + BRA.U.ANY serialisation it emits in divergent code.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -89,8 +89,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     const int tiles_per_img = g.tiles_w * g.tiles_h;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
+        {
+            // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
@@ -109,6 +109,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem_a + stage * UMMA_A_BYTES;
                     uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
@@ -132,14 +133,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         else tma_load_4d(sa, &mapA2, &full_bar[stage], (k1 - g.cch1a) * 64, w0, h0, n0);
                     }
                     tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, sp * p.Cout + nt * BN);
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
+        {
+            // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
             constexpr uint32_t idesc = umma_idesc_bf16(UMMA_BM, BN);
             uint32_t stage = 0, phase = 0, it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -150,15 +153,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * UMMA_A_BYTES));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+                    if (elect_one()) {
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * UMMA_A_BYTES));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)  // 4 x (K = 16) per 64-channel chunk: +32 bytes = +2 in descriptor units
-                        umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
-                    umma_commit(&empty_bar[stage]);
+                        for (int j = 0; j < 4; ++j)  // 4 x (K = 16) per 64-channel chunk: +32 bytes = +2 in descriptor units
+                            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == nkb - 1) umma_commit(&tfull_bar[as]);
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[as]);
             }
         }
         __syncwarp();

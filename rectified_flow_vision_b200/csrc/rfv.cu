@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "conv_mma.cuh"
 #include "conv_params.h"
+#include "conv_halo.cuh"
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
@@ -121,7 +122,8 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true;
+    bool keep_acts = false, use_umma = true, use_halo = true;
+    int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
 
     std::vector<void*> allocs;
@@ -338,7 +340,56 @@ struct rfv_engine {
         const bool umma_ok = use_umma && pow2 && (!L->ups || L->subpixel) && L->C0 % 64 == 0 && L->C1a % 64 == 0 &&
                              L->C1b % 64 == 0 && L->Cout % 64 == 0 && gH * gW >= 64 && gW >= 8 && (L->stride == 1 || sc.empty());
         if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
-        if (umma_ok) {
+        const bool halo_ok = umma_ok && use_halo && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
+                             (out->W == 32 || out->W == 64 || out->W == 128);
+        if (halo_ok) {
+            struct HBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; int BN; size_t smem; };
+            auto bd = std::make_shared<HBundle>();
+            HaloGeom& g = bd->g;
+            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
+            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
+            g.tiles_per_img = (g.H * g.pitch + 127) / 128;
+            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+            const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
+            bd->BN = BN;
+            g.n_tiles = L->Cout / BN;
+            g.a_box_bytes = g.rows * g.pitch * 128;
+            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
+            g.base_offset_mode = base_offset_mode;
+            const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
+            const int avail = 227 * 1024 - 2048 - 512;
+            const int bbytes = BN * 128;
+            g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
+            int bregion;
+            if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
+            else { g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8); bregion = g.b_stages * bbytes; }
+            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
+            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
+            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 512;
+            auto amap = [&](CUtensorMap* m, const ActP& t) {
+                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
+            };
+            RFV_TRY(amap(&bd->a0, in0));
+            bd->a1 = bd->a0; bd->a2 = bd->a0;
+            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
+            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            const int sms = num_sms, sumC_ = sumC;
+            push("conv_halo", "conv:" + L->name, fl, [p, bd, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+                ConvParams q = p;
+                q.B = rc.B;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                HaloGeom g = bd->g;
+                g.m_tiles = rc.B * g.tiles_per_img;
+                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
+                switch (bd->BN) {
+                    case 256: conv_halo_kernel<256><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g); break;
+                    case 128: conv_halo_kernel<128><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g); break;
+                    default: conv_halo_kernel<64><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                }
+                return cudaGetLastError();
+            });
+        } else if (umma_ok) {
             struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
@@ -710,6 +761,9 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
 }
 
@@ -778,6 +832,8 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->cap = (cfg->micro_batch + 1) & ~1;
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
+    e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
+    e->base_offset_mode = (cfg->flags & RFV_FLAG_BASEOFF) ? 1 : 0;
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
     {

@@ -22,8 +22,9 @@ def main():
     ap.add_argument("--no-umma", action="store_true")
     ap.add_argument("--case", default="small32")
     ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--flags", type=int, default=0, help="extra RFV_FLAG_* bits")
     a = ap.parse_args()
-    flags = 4 | (1 if a.no_umma else 0)
+    flags = 4 | (1 if a.no_umma else 0) | a.flags
     m = util.seeded_model(a.case)
     g = util.golden(a.case)
     spec = util.spec_for(a.case)
