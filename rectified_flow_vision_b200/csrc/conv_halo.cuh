@@ -75,7 +75,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], UMMA_THREADS - 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
         mbar_fence_init();
     }
     // the row after each box must read as zero (tap (+1,+1) of the last pixel of the last box row lands there)
@@ -213,76 +213,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        // ===================== epilogue: warp-group g drains accumulator stage g (tiles it = g, g+2, ...) =====================
+        const int q = warp & 3, grp = (warp - 4) >> 2;
         const int r = q * 32 + lane;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        uint32_t it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
             const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
             const int n = mt / g.tiles_per_img, ti = mt - n * g.tiles_per_img;
             const int pos = ti * 128 + r;
             const int rr = pos / g.pitch, cc = pos - rr * g.pitch;
-            const bool valid = n < p.B && cc >= 1 && rr < g.H;
+            const bool n_ok = n < p.B;
+            const bool valid = n_ok && cc >= 1 && rr < g.H;
             const size_t pix = ((size_t)n * g.H + rr) * g.W + (cc - 1);
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-            for (int ch = half; ch < BN / 32; ch += 2) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + ch * 32, acc);
-                tmem_ld_wait();
-                if (ch + 2 >= BN / 32) {
-                    tc_fence_before();
-                    mbar_arrive(&tempty[as]);
-                }
-                const int c0 = nt * BN + ch * 32;
-                float v[32];
-                {
-                    const float* add = p.temb ? p.temb + (size_t)(n < p.B ? n : 0) * p.temb_stride + c0 : p.bias + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(add + i);
-                        v[i] = __uint_as_float(acc[i]) + b4.x;
-                        v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
-                        v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
-                        v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
-                    }
-                }
-                if (p.resid && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.Cout + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float f[8];
-                        unpack8(rp[i], f);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[i * 8 + j] += f[j];
-                    }
-                }
-                if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = pack8(v + i * 8);
-                }
-                if (p.stats) {
-                    float t8[8];
-#pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) {
-                        float s = 0.f, ss = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float x = valid ? v[sl * 8 + j] : 0.f; s += x; ss += x * x; }
-                        t8[sl * 2] = s;
-                        t8[sl * 2 + 1] = ss;
-                    }
-                    warp_reduce8(t8, lane);
-                    if ((lane & 3) == 0 && n < p.B) {
-                        const int idx = lane >> 2;
-                        float* dst = p.stats + ((size_t)n * (p.Cout >> p.slab_shift) + ((c0 + (idx >> 1) * 8) >> p.slab_shift)) * 2;
-                        atomicAdd(dst + (idx & 1), t8[0]);
-                    }
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+            conv_epilogue_tile<BN>(p, taddr, n, n_ok, valid, pix, nt, lane, &tfull[grp], (it >> 1) & 1, &tempty[grp]);
         }
     }
     tc_fence_before();

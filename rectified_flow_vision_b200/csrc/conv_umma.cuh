@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 #include "conv_params.h"
 
 namespace rfv {
@@ -71,7 +72,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], UMMA_THREADS - 128);
+            mbar_init(&tempty_bar[s], 128);
         }
         mbar_fence_init();
     }
@@ -169,13 +170,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
+        // ===================== epilogue: warp-group g drains accumulator stage g (tiles it = g, g+2, ...) =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access (warp id mod 4)
-        const int half = (warp - 4) >> 2;       // which interleaved half of the 32-column chunks this warp drains
+        const int grp = (warp - 4) >> 2;
         const int r = q * 32 + lane;            // row of the tile = output pixel
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        uint32_t it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
             const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
             const int mt = rest / phases, sp = rest - mt * phases;
             int n, h, w;
@@ -189,87 +189,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 h = (r >> g.bw_shift) & ((1 << g.bh_shift) - 1);
                 w = r & ((1 << g.bw_shift) - 1);
             }
-            const bool valid = n < p.B;
             if (g.ups) { h = 2 * h + (sp >> 1); w = 2 * w + (sp & 1); }
+            const bool valid = n < p.B;
             const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-            for (int ch = half; ch < BN / 32; ch += 2) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + ch * 32, acc);
-                tmem_ld_wait();
-                if (ch + 2 >= BN / 32) {  // this thread's last chunk is in registers: hand its share of the TMEM stage back
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[as]);
-                }
-                const int c0 = nt * BN + ch * 32;
-                float v[32];
-                {   // per-channel addend: the conv bias, or (bias + time projection) pre-summed by the temb kernel
-                    const float* add = p.temb ? p.temb + (size_t)(valid ? n : 0) * p.temb_stride + c0 : p.bias + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(add + i);
-                        v[i] = __uint_as_float(acc[i]) + b4.x;
-                        v[i + 1] = __uint_as_float(acc[i + 1]) + b4.y;
-                        v[i + 2] = __uint_as_float(acc[i + 2]) + b4.z;
-                        v[i + 3] = __uint_as_float(acc[i + 3]) + b4.w;
-                    }
-                }
-                if (p.resid && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.Cout + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float f[8];
-                        unpack8(rp[i], f);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[i * 8 + j] += f[j];
-                    }
-                }
-                if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) op[i] = pack8(v + i * 8);
-                }
-                if (p.stats) {
-                    // a warp's 32 rows always lie inside one image (Ho*Wo % 32 == 0)
-                    // 8 partial sums per lane (4 slabs x {sum, sum of squares}) -> transposing butterfly: 9 shuffles,
-                    // after which lane L (L % 4 == 0) holds the warp total of value (L >> 2)
-                    float t8[8];
-#pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) {
-                        float s = 0.f, ss = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float x = valid ? v[sl * 8 + j] : 0.f; s += x; ss += x * x; }
-                        t8[sl * 2] = s;
-                        t8[sl * 2 + 1] = ss;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float send = (lane & 16) ? t8[i] : t8[i + 4], keep = (lane & 16) ? t8[i + 4] : t8[i];
-                        t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float send = (lane & 8) ? t8[i] : t8[i + 2], keep = (lane & 8) ? t8[i + 2] : t8[i];
-                        t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-                    {
-                        const float send = (lane & 4) ? t8[0] : t8[1], keep = (lane & 4) ? t8[1] : t8[0];
-                        t8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    t8[0] += __shfl_xor_sync(0xffffffffu, t8[0], 2);
-                    t8[0] += __shfl_xor_sync(0xffffffffu, t8[0], 1);
-                    const int n_w = __shfl_sync(0xffffffffu, n, 0);
-                    const bool v_w = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
-                    if ((lane & 3) == 0 && v_w) {
-                        const int idx = lane >> 2;  // value index: slab = idx >> 1, {sum, sumsq} = idx & 1
-                        float* dst = p.stats + ((size_t)n_w * (p.Cout >> p.slab_shift) + ((c0 + (idx >> 1) * 8) >> p.slab_shift)) * 2;
-                        atomicAdd(dst + (idx & 1), t8[0]);
-                    }
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+            conv_epilogue_tile<BN>(p, taddr, n, valid, valid, pix, nt, lane, &tfull_bar[grp], (it >> 1) & 1, &tempty_bar[grp]);
         }
     }
     tc_fence_before();
