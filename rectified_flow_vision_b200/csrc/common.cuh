@@ -133,6 +133,24 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* map, uint64_
         : "memory");
 }
 
+// Multicast variant: the box lands at the same shared-memory offset in every CTA of `mask` and completes bytes on the
+// mbarrier at the same offset in each of them (weights shared by the CTAs of a cluster are fetched from L2 once).
+__device__ __forceinline__ void tma_load_2d_mc(void* smem, const void* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, load
 // ---------------------------------------------------------------------------------------------------------
@@ -159,6 +177,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed (implies fence::before).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Same, arriving on the barrier at this offset in every CTA of `mask` (a multicast-filled stage is free only when all
+// CTAs of the cluster have consumed it).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i).

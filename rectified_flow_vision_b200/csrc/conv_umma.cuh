@@ -29,6 +29,8 @@ struct UmmaGeom {
     int taps;                 // 9, 1, or 4 (sub-pixel phases of a nearest-x2-upsample + 3x3 conv)
     int stride2;              // 1: segment 0 reads the four parity maps
     int ups;                  // 1: output is 2x the input; tiles enumerate (pixel box, phase py/px, channel tile)
+    int cluster;              // CTAs per cluster (1, 2 or 4): they run m-tiles cl*g+rank of the same (phase, n-tile) in
+                              // lock-step and each multicasts 1/cluster of the weight slice to all of them
 };
 
 constexpr int UMMA_BM = 128;
@@ -62,13 +64,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int CL = g.cluster;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);  // one arrival per CTA of the cluster (multicast commit)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
@@ -79,13 +84,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int nkb0 = g.taps * g.cch0;
     const int nkb = nkb0 + g.cch1a + g.cch1b;
     const int phases = g.ups ? 4 : 1;
-    const int total_tiles = g.m_tiles * g.n_tiles * phases;
+    // Tiles are enumerated per cluster: "super-tile" = (group of CL consecutive m-tiles, phase, n-tile); CTA `crank`
+    // takes m-tile group*CL + crank.  m-tiles past the end are computed on zero-filled boxes and never stored.
+    const int m_groups = (g.m_tiles + CL - 1) / CL;
+    const int total_tiles = m_groups * g.n_tiles * phases;
+    const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
     const int box_shift = g.bw_shift + g.bh_shift;        // log2 pixels per image inside a box
     const int tiles_per_img = g.tiles_w * g.tiles_h;
 
@@ -93,9 +103,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         {
             // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
-                const int mt = rest / phases, sp = rest - mt * phases;  // sp: sub-pixel phase of an upsample conv
+                const int mt = (rest / phases) * CL + crank, sp = rest % phases;  // sp: sub-pixel phase of an upsample conv
                 const int py = sp >> 1, px = sp & 1;
                 int n0, h0, w0;
                 if (box_shift >= 7) {
@@ -133,7 +143,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         if (k1 < g.cch1a) tma_load_4d(sa, &mapA1, &full_bar[stage], k1 * 64, w0, h0, n0);
                         else tma_load_4d(sa, &mapA2, &full_bar[stage], (k1 - g.cch1a) * 64, w0, h0, n0);
                     }
-                    tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, sp * p.Cout + nt * BN);
+                    if (CL == 1) tma_load_2d(sb, &mapW, &full_bar[stage], kb * 64, sp * p.Cout + nt * BN);
+                    else  // this CTA's 1/CL of the weight rows, delivered to every CTA of the cluster
+                        tma_load_2d_mc(sb + crank * (Cfg::B_BYTES / CL), &mapW, &full_bar[stage], kb * 64,
+                                       sp * p.Cout + nt * BN + crank * (BN / CL), cmask);
                     }
                     __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -146,7 +159,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
             constexpr uint32_t idesc = umma_idesc_bf16(UMMA_BM, BN);
             uint32_t stage = 0, phase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
@@ -160,7 +173,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 4; ++j)  // 4 x (K = 16) per 64-channel chunk: +32 bytes = +2 in descriptor units
                             umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kb | j) != 0);
-                        umma_commit(&empty_bar[stage]);
+                        if (CL == 1) umma_commit(&empty_bar[stage]);
+                        else umma_commit_mc(&empty_bar[stage], cmask);
                         if (kb == nkb - 1) umma_commit(&tfull_bar[as]);
                     }
                     __syncwarp();
@@ -175,9 +189,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         const int grp = (warp - 4) >> 2;
         const int r = q * 32 + lane;            // row of the tile = output pixel
         uint32_t it = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+        for (int tile = tile0 + grp * tile_step; tile < total_tiles; tile += 2 * tile_step, it += 2) {
             const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
-            const int mt = rest / phases, sp = rest - mt * phases;
+            const int mt = (rest / phases) * CL + crank, sp = rest % phases;
             int n, h, w;
             if (box_shift >= 7) {
                 n = mt / tiles_per_img;
@@ -198,6 +212,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // nobody exits while a peer may still multicast into / arrive on its shared memory
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

@@ -123,6 +123,7 @@ struct rfv_engine {
     int slab_shift = 3;
     int td = 256, sumC = 0;
     bool keep_acts = false, use_umma = true, use_halo = true;
+    int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
 
@@ -390,7 +391,7 @@ struct rfv_engine {
                 return cudaGetLastError();
             });
         } else if (umma_ok) {
-            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; };
+            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
             const int bw = std::min(gW, 128), bh = std::min(gH, 128 / bw), bn = 128 / (bw * bh);
@@ -421,7 +422,25 @@ struct rfv_engine {
                         RFV_TRY(make_map4(mp[ph * 2 + pw], in0->p + ((size_t)ph * Wi + pw) * C, C, Wi / 2, Hi / 2, capN,
                                           (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
             }
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN));
+            g.cluster = cluster;
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN / g.cluster));
+            bd->max_clusters = num_sms / g.cluster;
+            if (g.cluster > 1) {  // how many clusters of this kernel can be co-resident (GPC boundaries strand SMs)
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3(num_sms / g.cluster * g.cluster);
+                lc.blockDim = dim3(UMMA_THREADS);
+                lc.dynamicSmemBytes = BN == 256 ? UmmaCfg<256>::SMEM_BYTES : (BN == 128 ? UmmaCfg<128>::SMEM_BYTES : UmmaCfg<64>::SMEM_BYTES);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                int nc = 0;
+                cudaError_t ce = BN == 256 ? cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<256>, &lc)
+                               : BN == 128 ? cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<128>, &lc)
+                                           : cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<64>, &lc);
+                if (ce != cudaSuccess || nc < 1) return fail(RFV_ERR_CUDA, "cudaOccupancyMaxActiveClusters failed: %s", cudaGetErrorString(ce));
+                bd->max_clusters = std::min(nc, num_sms / g.cluster);
+            }
             const int sms = num_sms;
             const int sumC_ = sumC;
             const int gHW = gH * gW;
@@ -431,19 +450,28 @@ struct rfv_engine {
                 q.temb_stride = rc.t ? sumC_ : 0;
                 UmmaGeom g = bd->g;
                 g.m_tiles = (int)(((size_t)rc.B * gHW + 127) / 128);
-                const int total = g.m_tiles * g.n_tiles * (g.ups ? 4 : 1);
-                const int grid = std::min(total, sms);
+                (void)sms;
+                const int super_tiles = ((g.m_tiles + g.cluster - 1) / g.cluster) * g.n_tiles * (g.ups ? 4 : 1);
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3(std::min(super_tiles, bd->max_clusters) * g.cluster);
+                lc.blockDim = dim3(UMMA_THREADS);
+                lc.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at;
+                lc.numAttrs = g.cluster > 1 ? 1 : 0;
                 switch (bd->BN) {
                     case 256:
-                        conv_umma_kernel<256><<<grid, UMMA_THREADS, UmmaCfg<256>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
-                        break;
+                        lc.dynamicSmemBytes = UmmaCfg<256>::SMEM_BYTES;
+                        return cudaLaunchKernelEx(&lc, conv_umma_kernel<256>, bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                     case 128:
-                        conv_umma_kernel<128><<<grid, UMMA_THREADS, UmmaCfg<128>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
-                        break;
+                        lc.dynamicSmemBytes = UmmaCfg<128>::SMEM_BYTES;
+                        return cudaLaunchKernelEx(&lc, conv_umma_kernel<128>, bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                     default:
-                        conv_umma_kernel<64><<<grid, UMMA_THREADS, UmmaCfg<64>::SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
+                        lc.dynamicSmemBytes = UmmaCfg<64>::SMEM_BYTES;
+                        return cudaLaunchKernelEx(&lc, conv_umma_kernel<64>, bd->a0, bd->a1, bd->a2, bd->a3, bd->w, q, g);
                 }
-                return cudaGetLastError();
             });
         } else {
             if (L->C0 % 8 != 0 || L->C1a % 8 != 0 || L->C1b % 8 != 0 || L->Cout % 64 != 0)
@@ -552,6 +580,13 @@ struct rfv_engine {
 // ---------------------------------------------------------------------------------------------------------
 int rfv_engine::build() {
     const int S = cfg.image_size, mc = cfg.model_channels, nlev = cfg.num_levels, nres = cfg.num_res_blocks;
+    // opt in to > 48 KB of dynamic shared memory first: the cluster-occupancy queries below depend on it
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
     std::vector<int> chans(nlev);
@@ -833,6 +868,11 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
+    {
+        const int c = (cfg->flags >> 8) & 7;
+        if (c == 1 || c == 2 || c == 4) e->cluster = c;
+        else if (c != 0) return fail(RFV_ERR_INVALID, "cluster size override must be 1, 2 or 4");
+    }
     e->base_offset_mode = (cfg->flags & RFV_FLAG_BASEOFF) ? 1 : 0;
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));

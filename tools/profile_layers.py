@@ -46,6 +46,12 @@ def main():
         key, ms, n, fl = ln.split("\t")
         rows.append((key, float(ms) / a.reps, float(fl) * a.mb))
     tot = sum(r[1] for r in rows)
+    kinds = {}
+    for key, ms, fl in rows:
+        k = kinds.setdefault(key.split(" ")[0], [0.0, 0.0])
+        k[0] += ms
+        k[1] += fl
+    print("  ".join(f"{k}={v[0]:.3f}ms" + (f"({v[1] / v[0] / 1e9:.0f}TF/s)" if v[1] > 0 else "") for k, v in sorted(kinds.items())))
     print(f"micro_batch={a.mb} size={a.size} flags={a.flags}: forward {fwd_ms:.3f} ms unprofiled, {tot:.3f} ms summed; "
           f"{a.mb / fwd_ms * 1e3:.0f} img-steps/s; {eng.flops_per_image() * a.mb / fwd_ms / 1e9:.1f} TFLOP/s")
     print(f"{'op':<52}{'ms':>9}{'share':>8}{'TFLOP/s':>10}")
