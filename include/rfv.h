@@ -60,6 +60,8 @@ typedef struct {
                                   B200: WRONG results -- the 128B swizzle is applied on absolute smem address bits, so
                                   shifted (128-byte aligned) start addresses need base offset 0.  Kept as an experiment. */
 
+#define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
+
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 int rfv_abi_version(void);
 const char* rfv_last_error(void);
@@ -107,6 +109,36 @@ int rfv_straightness(rfv_handle h, const float* x0, const float* x1, int64_t bat
  * network.  loss_out: 1 fp32 DEVICE value. */
 int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch,
                 float* loss_out, void* stream);
+
+/* ---- training: the body of train_rectified_flow / train_base_flow (models/rectified_flow.py:217-238,
+ *      models/base_flow.py:266-275): loss = mse(v(x_t,t), x1-x0); loss.backward(); clip_grad_norm_(1.0); AdamW.step().
+ *      Needs RFV_FLAG_TRAIN.  The pieces are separate so a data-parallel caller can all-reduce the flat gradient
+ *      buffer between rfv_train_accumulate and rfv_optimizer_step (models have no collective in the reference). -- */
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay;  /* torch.optim.AdamW: 1e-4 (caller), 0.9, 0.999, 1e-8, 0.01 */
+    float max_grad_norm;                        /* clip_grad_norm_ threshold (1.0 in the reference); <= 0: no clipping */
+    float grad_scale;                           /* applied to every gradient first (1/world_size after a SUM all-reduce) */
+    int64_t step;                               /* 1-based optimizer step (bias correction) */
+} rfv_adamw;
+
+/* Zero the flat gradient buffer (optimizer.zero_grad()). */
+int rfv_zero_grad(rfv_handle h, void* stream);
+/* Forward + backward of mean((v((1-t) x0 + t x1, t) - (x1 - x0))^2) over `batch` rows, training-mode network
+ * (dropout_p as in the model constructor, 0.1 in the reference; mask from a counter-based generator keyed by
+ * `seed`).  Parameter gradients are ADDED into the flat buffer; loss_out (1 fp32 DEVICE value) receives the mean
+ * loss of this call.  Batches larger than the micro-batch are processed in chunks (gradient accumulation). */
+int rfv_train_accumulate(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch,
+                         float dropout_p, uint64_t seed, float* loss_out, void* stream);
+/* The flat fp32 gradient buffer (device memory owned by the engine; one slot per parameter tensor in
+ * rfv_tensor_info order; conv-weight slots are laid out [O][kh*kw][I]). */
+int rfv_grad_buffer(rfv_handle h, float** dev_ptr, int64_t* numel);
+/* One parameter's gradient, scaled, in reference layout (tests / debugging). */
+int rfv_get_grad(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, float scale, void* stream);
+/* Make the optimizer also write updated values into caller-owned fp32 storage (the torch Parameter). */
+int rfv_bind_param(rfv_handle h, const char* name, float* dev_ptr);
+/* Global-norm clip + AdamW update of every parameter from the flat gradient buffer, then refresh of the packed
+ * bf16 copies.  grad_norm_out (optional, DEVICE): the pre-clip global gradient norm. */
+int rfv_optimizer_step(rfv_handle h, const rfv_adamw* hyper, float* grad_norm_out, void* stream);
 
 /* ---- introspection for tests / bench -------------------------------------------------------------------- */
 /* Number of engine kernels launched (or graph-replayed) since the last call with reset != 0. */

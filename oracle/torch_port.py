@@ -41,9 +41,9 @@ def _attn(P, pre, x, heads=4):
     return x + F.conv2d(o, P[pre + "proj.weight"], P[pre + "proj.bias"])
 
 
-@torch.no_grad()
-def unet_forward(P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor, model_channels: int = 64,
-                 channel_mult: Sequence[int] = (1, 2, 4), num_res_blocks: int = 2, pre: str = "velocity_net."):
+def unet_forward_grad(P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor, model_channels: int = 64,
+                      channel_mult: Sequence[int] = (1, 2, 4), num_res_blocks: int = 2, pre: str = "velocity_net."):
+    """The forward pass without the no_grad guard (oracle/train_oracle.py differentiates through it)."""
     half = model_channels // 2
     freqs = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
     arg = t[:, None] * freqs[None, :]
@@ -74,6 +74,11 @@ def unet_forward(P: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor, m
                          P[f"{pre}upsamples.{li}.1.bias"], padding=1)
     h = F.silu(F.group_norm(h, 8, P[pre + "output_conv.0.weight"], P[pre + "output_conv.0.bias"]))
     return F.conv2d(h, P[pre + "output_conv.2.weight"], P[pre + "output_conv.2.bias"], padding=1)
+
+
+@torch.no_grad()
+def unet_forward(P, x, t, **kw):
+    return unet_forward_grad(P, x, t, **kw)
 
 
 @torch.no_grad()

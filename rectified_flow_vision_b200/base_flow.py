@@ -9,8 +9,9 @@ reference (``models/base_flow.py:24-226``); the numerical bodies are single call
   compute_loss           -> rfv_fm_loss         (models/base_flow.py:113-129; forward value only, see below)
   save / load            -> unchanged torch.save / torch.load of {'state_dict','config'} (models/base_flow.py:210-226)
 
-Not native yet: the backward pass.  ``compute_loss`` returns the loss VALUE (no autograd graph) and the
-``train_*`` loops raise ``NotImplementedError`` instead of silently training through PyTorch.
+``compute_loss`` returns the loss VALUE (no autograd graph: the backward pass is native too, driven by
+``train_base_flow`` / ``train_rectified_flow`` through ``training.NativeTrainer`` -- rfv_train_accumulate +
+rfv_optimizer_step -- never through PyTorch autograd).
 """
 from __future__ import annotations
 
@@ -52,7 +53,7 @@ class BaseFlowModel(nn.Module):
 
     def compute_loss(self, x1: torch.Tensor) -> torch.Tensor:
         """Flow-matching loss value for a data batch (models/base_flow.py:104-131): fresh x0 ~ N(0,I),
-        t ~ U[0,1).  Returned tensor carries no autograd graph (native backward: not implemented yet)."""
+        t ~ U[0,1).  Returned tensor carries no autograd graph (training goes through ``train_base_flow``)."""
         x0 = torch.randn_like(x1)
         t = torch.rand(x1.shape[0], device=x1.device)
         return self._engine(x1.shape[-1]).fm_loss(x0, x1, t)
@@ -98,7 +99,28 @@ class BaseFlowModel(nn.Module):
 
 def train_base_flow(model: BaseFlowModel, dataloader, epochs: int = 50, lr: float = 1e-4,
                     save_path: Optional[str] = None, save_every: int = 10) -> List[float]:
-    """models/base_flow.py:229-295.  Needs the native backward + AdamW step."""
-    raise NotImplementedError(
-        "train_base_flow: the native backward/optimizer step is not implemented yet; this package does not "
-        "fall back to PyTorch autograd.  Use the reference trainer to produce checkpoints and load() them.")
+    """models/base_flow.py:229-295: flow matching on real data, x0 ~ N(0, I) and t ~ U[0,1) drawn per batch
+    (``compute_loss``, :113-129); step body on the native engine (see ``training.NativeTrainer``)."""
+    import numpy as np
+    from .training import NativeTrainer, cosine_lr
+
+    trainer = NativeTrainer(model, lr=lr)
+    losses: List[float] = []
+    for epoch in range(epochs):
+        model.train()
+        cur_lr = cosine_lr(lr, epoch, epochs)
+        epoch_losses = []
+        for batch in dataloader:
+            x = batch[0] if isinstance(batch, (list, tuple)) else batch
+            x = x.to(model.device)
+            x0 = torch.randn_like(x)
+            t = torch.rand(x.shape[0], device=x.device)
+            epoch_losses.append(trainer.step(x0, x, t, lr=cur_lr))
+        avg_loss = float(torch.stack(epoch_losses).mean().item())
+        losses.append(avg_loss)
+        print(f"Epoch {epoch+1}/{epochs} - Loss: {avg_loss:.4f}")
+        if save_path and (epoch + 1) % save_every == 0:
+            model.save(f"{save_path}_epoch{epoch+1}.pt")
+    if save_path:
+        model.save(f"{save_path}_final.pt")
+    return losses

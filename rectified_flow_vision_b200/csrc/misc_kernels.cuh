@@ -3,6 +3,7 @@
 // weight packing, flow-matching interpolation.
 #pragma once
 #include "common.cuh"
+#include "train_kernels.cuh"
 
 namespace rfv {
 
@@ -14,7 +15,10 @@ namespace rfv {
 __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, int t_stride_is_zero, float t_scalar,
                                                    const float* __restrict__ w1, const float* __restrict__ b1,
                                                    const float* __restrict__ w2, const float* __restrict__ b2,
-                                                   float* __restrict__ out, int mc, int td) {
+                                                   float* __restrict__ out, int mc, int td, float* __restrict__ save_emb,
+                                                   float* __restrict__ save_z1, float* __restrict__ save_h1,
+                                                   float* __restrict__ save_z2) {
+    // save_*: training only -- the sinusoidal embedding and the two pre-activations, read by the time-MLP backward
     extern __shared__ float sm[];
     float* emb = sm;        // [mc]
     float* h1 = sm + mc;    // [td]
@@ -29,19 +33,27 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
         emb[j + half] = cosf(a);
     }
     __syncthreads();
+    if (save_emb)
+        for (int j = threadIdx.x; j < mc; j += blockDim.x) save_emb[(size_t)b * mc + j] = emb[j];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int o = warp; o < td; o += nw) {
         float s = 0.f;
         for (int j = lane; j < mc; j += 32) s += w1[(size_t)o * mc + j] * emb[j];
         s = warp_sum(s);
-        if (lane == 0) h1[o] = silu_f(s + b1[o]);
+        if (lane == 0) {
+            h1[o] = silu_f(s + b1[o]);
+            if (save_z1) { save_z1[(size_t)b * td + o] = s + b1[o]; save_h1[(size_t)b * td + o] = h1[o]; }
+        }
     }
     __syncthreads();
     for (int o = warp; o < td; o += nw) {
         float s = 0.f;
         for (int j = lane; j < td; j += 32) s += w2[(size_t)o * td + j] * h1[j];
         s = warp_sum(s);
-        if (lane == 0) out[(size_t)b * td + o] = silu_f(s + b2[o]);
+        if (lane == 0) {
+            out[(size_t)b * td + o] = silu_f(s + b2[o]);
+            if (save_z2) save_z2[(size_t)b * td + o] = s + b2[o];
+        }
     }
 }
 
@@ -176,7 +188,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ stats_a, const float* __restrict__ stats_b,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        bf16* __restrict__ out, int Ca, int Cb, int HW, int slab_shift,
-                                                       int apply_silu, int pix_per_block, float eps) {
+                                                       int apply_silu, int pix_per_block, float eps, uint32_t drop_thresh,
+                                                       uint32_t drop_seed, float drop_scale) {
+    // drop_thresh != 0 (training only): nn.Dropout after the SiLU (models/unet.py:62), mask from train_kernels.cuh
     // blockDim.x is a multiple of C/8, so every thread owns ONE 8-channel vector position for the whole block and
     // keeps its scale/shift in registers; the streaming loop is then load -> 8 FMAs (+SiLU) -> store.
     extern __shared__ float sm[];
@@ -242,6 +256,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                     const float y = fmaf(f[j], sc[j], sh[j]);
                     f[j] = apply_silu ? silu_f(y) : y;
                 }
+                if (drop_thresh) {
+                    float mk[8];
+                    dropout_mask8(drop_seed, (uint32_t)((base + px) * C + cv * 8), drop_thresh, drop_scale, mk);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] *= mk[j];
+                }
                 *reinterpret_cast<uint4*>(out + (base + px) * C + cv * 8) = pack8(f);
             }
         }
@@ -253,6 +273,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 //   mode 0  v = conv(a)                                      (UNet.forward result, models/unet.py:275)
 //   mode 1  x += dt * conv(a)   [+ snapshot into traj]       (Euler update, models/base_flow.py:170)
 //   mode 2  nothing is written (loss only)
+//   mode 3  xv = (conv(a) - (x1 - x0)) * dt : the loss gradient w.r.t. the prediction (dt carries 2 / numel)
 // and optionally accumulates sum((conv(a) - target)^2), target = x1 - x0, for the loss / straightness metrics
 // (models/rectified_flow.py:118,231).  a: NHWC bf16 (already GroupNorm+SiLU'd); x, v, x0, x1: NCHW fp32.
 // Tensor-core formulation: per 8x32-pixel tile the halo of `a` is staged in shared memory (cp.async, double
@@ -341,6 +362,7 @@ __global__ void __launch_bounds__(256) output_conv_kernel(const bf16* __restrict
                         const size_t o = (((size_t)n * Cout + co) * H + h) * W + w;
                         if (mse_acc) { const float d = val - (x1[o] - x0[o]); sq += d * d; }
                         if (mode == 0) xv[o] = val;
+                        else if (mode == 3) xv[o] = (val - (x1[o] - x0[o])) * dt;
                         else if (mode == 1) {
                             const float nx = xv[o] + val * dt;
                             xv[o] = nx;

@@ -26,6 +26,8 @@
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
+#include "train_kernels.cuh"
+#include "wgrad.cuh"
 
 #define RFV_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -66,6 +68,9 @@ struct Act {  // NHWC bf16 activation of the current micro-batch
     float* stats = nullptr;  // [cap][C/slab][2]
     size_t bytes = 0;
     int refs = 0;
+    bf16* grad = nullptr;    // training: dL/d(this tensor), same layout
+    int consumers = 0;       // training: number of differentiable consumers (the last one, in forward order, runs first
+                             // in the backward pass and overwrites `grad`; the others accumulate)
 };
 typedef std::shared_ptr<Act> ActP;
 
@@ -76,6 +81,9 @@ struct Param {  // one reference state_dict tensor
     bool loaded = false;
     std::function<int(cudaStream_t)> repack;  // refresh derived buffers after upload
     std::function<int(float*, cudaStream_t)> readback;  // optional: reconstruct fp32 from the packed form
+    int64_t goff = 0;        // training: offset of this tensor's slot in the flat gradient / Adam-moment buffers
+    int O = 0, I = 0, KK = 0;  // conv weights (KK > 1): the slot is laid out [O][KK][I] (what the wgrad kernel writes)
+    float* bound = nullptr;  // caller-owned fp32 storage (torch Parameter) the optimizer also writes
 };
 
 struct RunCtx {
@@ -91,6 +99,10 @@ struct RunCtx {
     float* mse = nullptr;
     int mode = 0;
     float dt = 0.f;
+    // training only
+    bool train = false;
+    uint32_t drop_thresh = 0, seed = 0;
+    float drop_scale = 1.f;
 };
 
 struct Op {
@@ -106,6 +118,7 @@ struct ConvLayer {
     bool subpixel = false;  // ups layer packed as 4 phases x (2x2 taps): w is [4*Cout][4*C0]
     bf16* w = nullptr;
     float* bias = nullptr;  // fused (conv bias + shortcut bias)
+    int iw = -1, ib = -1, isw = -1, isb = -1;  // parameter indices (weight, bias, shortcut weight, shortcut bias)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -164,6 +177,29 @@ struct rfv_engine {
         have_last = true;
         return 0;
     }
+
+    // ----- training state (RFV_FLAG_TRAIN) ---------------------------------------------------------------------
+    bool train = false;
+    std::vector<Op>* rec = &ops;                 // list that push() appends to
+    std::vector<std::vector<Op>> bwd_blocks;     // one per forward stage, executed back to front
+    float *gflat = nullptr, *mflat = nullptr, *vflat = nullptr;  // flat gradient / Adam moments, slot order = parameter order
+    int64_t gtotal = 0;
+    float* cs_arena = nullptr;                   // GroupNorm-backward per-(image, channel) sums, one slice per norm site
+    size_t cs_floats = 0, cs_used = 0;
+    bf16* scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_elems = 0;                    // per image
+    float *d_tproj = nullptr, *temb_emb = nullptr, *temb_z1 = nullptr, *temb_h1 = nullptr, *temb_z2 = nullptr;
+    float *d_tz2 = nullptr, *d_tz1 = nullptr;
+    float *dv_buf = nullptr, *lse = nullptr, *delta = nullptr, *zero_bias = nullptr, *norm2 = nullptr;
+    AdamSeg* d_segs = nullptr;
+    int2* d_adam_blocks = nullptr;
+    int n_adam_blocks = 0;
+    bool adam_dirty = true;
+    int norm_sites = 0;
+    struct TimeProj { int off, Cout, iw, ib, icb; };
+    std::vector<TimeProj> time_projs;
+    struct BwdProf { const Op* op; cudaEvent_t e0, e1; };
+    std::vector<BwdProf> bwd_prof;
 
     int64_t launches = 0;
     double flops_per_image = 0;
@@ -225,6 +261,8 @@ struct rfv_engine {
         p.name = "velocity_net." + name;
         p.numel = numel;
         RFV_TRY(dalloc(&p.f32, (size_t)numel));
+        p.goff = gtotal;
+        gtotal += numel;
         param_index[p.name] = (int)params.size();
         *idx = (int)params.size();
         params.push_back(std::move(p));
@@ -247,10 +285,13 @@ struct rfv_engine {
         RFV_TRY(add_param(name + ".bias", Cout, &ib));
         ConvLayer* l = L.get();
         const int C1 = C1a + C1b;
+        if (ks > 1) { params[iw].O = Cout; params[iw].I = C0; params[iw].KK = ks * ks; }
+        l->iw = iw; l->ib = ib;
         if (C1 > 0) {
             RFV_TRY(add_param(sc_name + ".weight", (int64_t)Cout * C1, &isw));
             RFV_TRY(add_param(sc_name + ".bias", Cout, &isb));
         }
+        l->isw = isw; l->isb = isb;
         params[iw].repack = [this, l, iw](cudaStream_t s) {
             if (l->subpixel) pack_upsample_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0);
             else pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
@@ -287,8 +328,8 @@ struct rfv_engine {
               std::function<cudaError_t(const RunCtx&, cudaStream_t)> fn) {
         Op op;
         op.kind = kind; op.label = label; op.flops = flops; op.run = std::move(fn);
-        flops_per_image += flops;
-        ops.push_back(std::move(op));
+        if (rec == &ops) flops_per_image += flops;
+        rec->push_back(std::move(op));
     }
 
     int make_map4(CUtensorMap* m, const bf16* base, int C, int Wd, int Hd, int Nd, size_t sW, size_t sH, size_t sN,
@@ -316,7 +357,12 @@ struct rfv_engine {
     }
 
     // Record one convolution.  in0: segment-0 input; sc: raw shortcut sources (0..2); resid: identity residual.
-    int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats) {
+    // acc_of / acc_k (training, gradient-producing convs): accumulate into `out` in place unless this is the first
+    // backward writer of acc_of's gradient, i.e. the last forward consumer (decided at run time: consumer counts are
+    // final only once the whole plan is built).
+    int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats,
+                ActP acc_of = nullptr, int acc_k = 0) {
+        const std::string pre = rec == &ops ? "conv:" : "bwd:dgrad:";
         ConvParams p{};
         p.out = out->p; p.a0 = in0->p;
         p.s1a = sc.size() > 0 ? sc[0]->p : nullptr;
@@ -376,9 +422,10 @@ struct rfv_engine {
             if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
             RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
             const int sms = num_sms, sumC_ = sumC;
-            push("conv_halo", "conv:" + L->name, fl, [p, bd, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
                 ConvParams q = p;
                 q.B = rc.B;
+                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
                 q.temb_stride = rc.t ? sumC_ : 0;
                 HaloGeom g = bd->g;
                 g.m_tiles = rc.B * g.tiles_per_img;
@@ -444,9 +491,10 @@ struct rfv_engine {
             const int sms = num_sms;
             const int sumC_ = sumC;
             const int gHW = gH * gW;
-            push("conv_umma", "conv:" + L->name, fl, [p, bd, gHW, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+            push("conv_umma", pre + L->name, fl, [p, bd, gHW, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
                 ConvParams q = p;
                 q.B = rc.B;
+                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
                 q.temb_stride = rc.t ? sumC_ : 0;
                 UmmaGeom g = bd->g;
                 g.m_tiles = (int)(((size_t)rc.B * gHW + 127) / 128);
@@ -478,9 +526,10 @@ struct rfv_engine {
                 return fail(RFV_ERR_INVALID, "conv %s: unsupported channel counts", L->name.c_str());
             const int sumC_ = sumC;
             const int cout = L->Cout;
-            push("conv_mma", "conv:" + L->name, fl, [p, HoWo, sumC_, cout](const RunCtx& rc, cudaStream_t s) {
+            push("conv_mma", pre + L->name, fl, [p, HoWo, sumC_, cout, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) {
                 ConvParams q = p;
                 q.B = rc.B;
+                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
                 q.temb_stride = rc.t ? sumC_ : 0;
                 dim3 grid((unsigned)(((size_t)rc.B * HoWo + MMA_BM - 1) / MMA_BM), cout / MMA_BN);
                 conv_mma_kernel<<<grid, 256, 0, s>>>(q);
@@ -490,11 +539,28 @@ struct rfv_engine {
         return 0;
     }
 
-    int gn_op(const std::string& name, std::vector<ActP> srcs, ActP out, bool silu) {
+    struct NormSite {  // what the GroupNorm backward needs to know about one forward norm
+        std::vector<ActP> srcs;
+        int ig = -1, ib = -1, C = 0, HW = 0, id = 0;
+        bool silu = false, drop = false;
+        float* cs = nullptr;  // [cap][C][2]
+    };
+    int gn_op(const std::string& name, std::vector<ActP> srcs, ActP out, bool silu, bool drop = false, NormSite* site = nullptr) {
         int ig, ib;
         const int C = out->C;
         RFV_TRY(add_param(name + ".weight", C, &ig));
         RFV_TRY(add_param(name + ".bias", C, &ib));
+        const int site_id = ++norm_sites;
+        if (site) {
+            site->srcs = srcs; site->ig = ig; site->ib = ib; site->C = C; site->HW = out->H * out->W; site->id = site_id;
+            site->silu = silu; site->drop = drop;
+            if (train) {
+                const size_t n = (size_t)cap * C * 2;
+                if (cs_used + n > cs_floats) return fail(RFV_ERR_NOMEM, "GroupNorm-backward arena exhausted");
+                site->cs = cs_arena + cs_used;
+                cs_used += n;
+            }
+        }
         const bf16* xa = srcs[0]->p;
         const bf16* xb = srcs.size() > 1 ? srcs[1]->p : nullptr;
         const float* sa = srcs[0]->stats;
@@ -514,7 +580,9 @@ struct rfv_engine {
         const int threads = (256 / vpp) * vpp;
         push("gn_apply", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             dim3 grid((HW + ppb - 1) / ppb, rc.B);
-            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb, 1e-5f);
+            const uint32_t dt_ = drop ? rc.drop_thresh : 0u;
+            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb, 1e-5f,
+                                                                         dt_, rc.seed ^ ((uint32_t)site_id * 0x9E3779B9u), rc.drop_scale);
             return cudaGetLastError();
         });
         return 0;
@@ -526,8 +594,10 @@ struct rfv_engine {
         for (auto& a : srcs) Cin += a->C;
         const int H = srcs[0]->H, W = srcs[0]->W;
         ActP a1, h, a2, out;
+        NormSite n1, n2;
+        const int ka = srcs[0]->consumers++, kb = srcs.size() > 1 ? srcs[1]->consumers++ : 0;
         RFV_TRY(new_act(&a1, Cin, H, W, false));
-        RFV_TRY(gn_op(name + ".norm1", srcs, a1, true));
+        RFV_TRY(gn_op(name + ".norm1", srcs, a1, true, false, &n1));
         ConvLayer *c1, *c2;
         RFV_TRY(add_conv(&c1, name + ".conv1", Cin, Cout, 3, 1, 0, "", 0, 0));
         RFV_TRY(new_act(&h, Cout, H, W, true));
@@ -537,6 +607,7 @@ struct rfv_engine {
         RFV_TRY(add_param(name + ".time_mlp.1.bias", Cout, &ib));
         const int off = *temb_cursor;
         *temb_cursor += Cout;
+        time_projs.push_back({off, Cout, iw, ib, param_index["velocity_net." + name + ".conv1.bias"]});
         params[iw].repack = [this, iw, off, Cout](cudaStream_t s) {
             cudaError_t e = cudaMemcpyAsync(wcat + (size_t)off * td, pf(iw), (size_t)Cout * td * sizeof(float), cudaMemcpyDeviceToDevice, s);
             return e == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "wcat copy failed");
@@ -555,7 +626,7 @@ struct rfv_engine {
         RFV_TRY(conv_op(c1, a1, {}, nullptr, h, off, true));
         release(a1);
         RFV_TRY(new_act(&a2, Cout, H, W, false));
-        RFV_TRY(gn_op(name + ".norm2", {h}, a2, true));
+        RFV_TRY(gn_op(name + ".norm2", {h}, a2, true, true, &n2));  // nn.Dropout follows this SiLU (models/unet.py:62)
         release(h);
         RFV_TRY(new_act(&out, Cout, H, W, true));
         if (Cin != Cout) {
@@ -568,10 +639,192 @@ struct rfv_engine {
         release(a2);
         named_acts[name] = out;
         *result = out;
+        if (train) {
+            // ---- backward of the block (models/unet.py:55-64 reversed); out->grad is complete when this runs ----
+            RFV_TRY(ensure_grad(out));
+            begin_bwd();
+            ActP dOut = grad_view(out), Tsc, Ta2, Th, Ta1;
+            ConvLayer *g1, *g2, *gs = nullptr;
+            RFV_TRY(add_dgrad_layer(&g2, c2, 0));
+            RFV_TRY(add_dgrad_layer(&g1, c1, 0));
+            if (Cin != Cout) {
+                RFV_TRY(add_dgrad_layer(&gs, c2, 1));
+                RFV_TRY(scratch_act(&Tsc, 0, Cin, H, W));
+                RFV_TRY(conv_op(gs, dOut, {}, nullptr, Tsc, -1, false));
+                RFV_TRY(bwd_wgrad(name + ".shortcut", 1, srcs[0], out->grad, Cout, W, H, c2->isw, Cin, 0));
+                if (srcs.size() > 1) RFV_TRY(bwd_wgrad(name + ".shortcut/b", 1, srcs[1], out->grad, Cout, W, H, c2->isw, Cin, srcs[0]->C));
+            }
+            RFV_TRY(bwd_wgrad(name + ".conv2", 0, a2, out->grad, Cout, W, H, c2->iw, 9 * Cout, 0));
+            bwd_colsum(name + ".conv2.bias", out->grad, Cout, H * W, nullptr, 0, c2->ib, c2->isb);
+            RFV_TRY(scratch_act(&Ta2, 1, Cout, H, W));
+            RFV_TRY(conv_op(g2, dOut, {}, nullptr, Ta2, -1, false));
+            RFV_TRY(scratch_act(&Th, 2, Cout, H, W));
+            RFV_TRY(bwd_gn(name + ".norm2", n2, Ta2->p, nullptr, nullptr, 0, 0, Th->p));
+            // d(time projection)[n][c] = sum over pixels of dh; conv1.bias and time_mlp.1.bias get its batch sum later
+            bwd_colsum(name + ".time", Th->p, Cout, H * W, d_tproj + off, sumC, -1, -1);
+            RFV_TRY(bwd_wgrad(name + ".conv1", 0, a1, Th->p, Cout, W, H, c1->iw, 9 * Cin, 0));
+            RFV_TRY(scratch_act(&Ta1, 1, Cin, H, W));
+            RFV_TRY(conv_op(g1, Th, {}, nullptr, Ta1, -1, false));
+            RFV_TRY(bwd_gn(name + ".norm1", n1, Ta1->p, Tsc ? Tsc->p : nullptr, Cin == Cout ? out->grad : nullptr, ka, kb));
+            end_bwd();
+        }
+        return 0;
+    }
+
+
+    // ===== training: backward recording (each forward stage appends one block; blocks run back to front) =====
+    void begin_bwd() { bwd_blocks.emplace_back(); rec = &bwd_blocks.back(); }
+    void end_bwd() { rec = &ops; }
+    float* gslot(int pi) { return gflat + params[pi].goff; }  // run time only (the flat buffer is allocated after the plan)
+
+    int ensure_grad(const ActP& a) {
+        if (a->grad) return 0;
+        return dalloc(&a->grad, a->bytes / sizeof(bf16));
+    }
+    ActP view(bf16* ptr, int C, int H, int W) {
+        auto a = std::make_shared<Act>();
+        a->p = ptr; a->C = C; a->H = H; a->W = W; a->refs = 1;
+        a->bytes = (size_t)cap * H * W * C * sizeof(bf16);
+        return a;
+    }
+    int scratch_act(ActP* out, int idx, int C, int H, int W) {
+        if ((size_t)C * H * W > scratch_elems) return fail(RFV_ERR_STATE, "internal: backward scratch too small for %dx%dx%d", C, H, W);
+        *out = view(scratch[idx], C, H, W);
+        return 0;
+    }
+    ActP grad_view(const ActP& a) { return view(a->grad, a->C, a->H, a->W); }
+
+    // Data-gradient twin of a forward conv: the same kernels on repacked weights.
+    // kind 0: segment 0 transposed + spatially flipped (3x3 or 1x1, stride 1); 1: the fused 1x1 shortcut segment
+    // transposed; 2: stride-2 conv as four sub-pixel phases over dY.
+    int add_dgrad_layer(ConvLayer** out, ConvLayer* src, int kind) {
+        auto L = std::make_unique<ConvLayer>();
+        const int C1 = src->C1a + src->C1b;
+        L->name = src->name + (kind == 1 ? "+shortcut" : "");
+        L->stride = 1;
+        if (kind == 0) { L->C0 = src->Cout; L->Cout = src->C0; L->ks = src->ks; L->K0 = L->ks * L->ks * L->C0; }
+        else if (kind == 1) { L->C0 = src->Cout; L->Cout = C1; L->ks = 1; L->K0 = L->C0; }
+        else { L->C0 = src->Cout; L->Cout = src->C0; L->ks = 3; L->ups = 1; L->subpixel = true; L->K0 = 4 * L->C0; }
+        L->Ktot = L->K0;
+        RFV_TRY(dalloc(&L->w, (size_t)L->Cout * L->Ktot * (L->subpixel ? 4 : 1)));
+        L->bias = zero_bias;
+        ConvLayer* l = L.get();
+        const int pi = kind == 1 ? src->isw : src->iw;
+        auto prev = params[pi].repack;
+        params[pi].repack = [this, prev, l, src, kind, pi, C1](cudaStream_t s) {
+            const int rc = prev ? prev(s) : 0;
+            if (rc) return rc;
+            if (kind == 0) pack_conv_weight_T_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0, src->ks * src->ks, 0, 0);
+            else if (kind == 1) pack_conv_weight_T_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, C1, 1, 0, 0);
+            else pack_down_dgrad_weight_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "dgrad weight pack launch failed");
+        };
+        *out = l;
+        convs.push_back(std::move(L));
+        return 0;
+    }
+
+    // dW slot of parameter `pi` (+)= wgrad(dy, a).  kind as make_wgrad_geom; a: the conv's input activations (for
+    // kind 2 the full-resolution tensor); dy: [cap, Ho, Wo, Cout].  The slot row holds ldw floats, this conv's columns
+    // start at koff_base (second source of a shortcut over a virtual concat).
+    int bwd_wgrad(const std::string& label, int kind, const ActP& a, const bf16* dy, int Cout, int Wo, int Ho, int pi, int ldw, int koff_base) {
+        struct Bundle { CUtensorMap ma[4], my; WgradGeom g; size_t smem; };
+        auto bd = std::make_shared<Bundle>();
+        if (a->C % 64 != 0 || Cout % 64 != 0) return fail(RFV_ERR_INVALID, "wgrad %s: channel counts must be multiples of 64", label.c_str());
+        if (!make_wgrad_geom(&bd->g, Wo, Ho, a->C, Cout, kind, ldw, koff_base)) return fail(RFV_ERR_INVALID, "wgrad %s: tile does not fit shared memory", label.c_str());
+        const WgradGeom& g = bd->g;
+        if (kind != 2) {
+            RFV_TRY(make_map4(&bd->ma[0], a->p, a->C, a->W, a->H, cap, a->C, (size_t)a->W * a->C, (size_t)a->H * a->W * a->C, g.pitch, g.R + 2, 1));
+            bd->ma[1] = bd->ma[2] = bd->ma[3] = bd->ma[0];
+        } else {
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw)
+                    RFV_TRY(make_map4(&bd->ma[ph * 2 + pw], a->p + ((size_t)ph * a->W + pw) * a->C, a->C, Wo, Ho, cap, (size_t)2 * a->C,
+                                      (size_t)2 * a->W * a->C, (size_t)a->H * a->W * a->C, g.pitch, g.R + 2, 1));
+        }
+        RFV_TRY(make_map4(&bd->my, dy, Cout, Wo, Ho, cap, Cout, (size_t)Wo * Cout, (size_t)Ho * Wo * Cout, g.pitch, g.R, 1));
+        bd->smem = wgrad_smem_bytes(g);
+        const int taps = kind == 1 ? 1 : 9;
+        const double fl = 2.0 * taps * a->C * Cout * Ho * Wo;
+        const int sms = num_sms;
+        push("wgrad_umma", "bwd:wgrad:" + label, fl, [this, bd, pi, sms](const RunCtx& rc, cudaStream_t s) {
+            WgradGeom g = bd->g;
+            g.num_tiles = rc.B * g.tiles_per_img;
+            const long long total = (long long)g.nvar * g.cchA * g.cchB * g.num_tiles;
+            const int grid = (int)std::min<long long>(total, sms);
+            wgrad_umma_kernel<<<grid, WG_THREADS, bd->smem, s>>>(bd->ma[0], bd->ma[1], bd->ma[2], bd->ma[3], bd->my, gslot(pi), g);
+            return cudaGetLastError();
+        });
+        return 0;
+    }
+
+    // per-(image, channel) sums of dy into out_nc (row stride ld_nc; may be null) and per-channel sums into up to two
+    // parameter-gradient slots (pi1 / pi2, -1: none)
+    void bwd_colsum(const std::string& label, const bf16* dy, int C, int HW, float* out_nc, int ld_nc, int pi1, int pi2) {
+        const int vpp = C / 8;
+        const int threads = (256 / vpp) * vpp;
+        const int ppb = std::min(HW, std::max(1, 32768 / C));
+        push("colsum", "bwd:colsum:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+            dim3 grid((HW + ppb - 1) / ppb, rc.B);
+            colsum_kernel<<<grid, threads, C * sizeof(float), s>>>(dy, out_nc, ld_nc, pi1 >= 0 ? gslot(pi1) : nullptr,
+                                                                   pi2 >= 0 ? gslot(pi2) : nullptr, C, HW, ppb);
+            return cudaGetLastError();
+        });
+    }
+
+    // GroupNorm(+SiLU)(+dropout) backward of `site`: gradients of its sources (+)= f(dy) + addends.
+    // ka / kb: consumer index this norm's block holds on srcs[0] / srcs[1]; out_override: write the (single-source)
+    // result there instead of srcs[0]->grad (intermediate tensors that have no gradient buffer of their own).
+    int bwd_gn(const std::string& label, const NormSite& st, const bf16* dy, const bf16* add_cat, const bf16* add_a, int ka, int kb,
+               bf16* out_override = nullptr) {
+        GnBwdArgs a{};
+        a.dy = dy;
+        a.xa = st.srcs[0]->p; a.stats_a = st.srcs[0]->stats; a.Ca = st.srcs[0]->C;
+        if (st.srcs.size() > 1) { a.xb = st.srcs[1]->p; a.stats_b = st.srcs[1]->stats; a.Cb = st.srcs[1]->C; }
+        a.gamma = pf(st.ig); a.beta = pf(st.ib);
+        a.cs = st.cs;
+        a.add_cat = add_cat; a.add_a = add_a;
+        if (out_override) a.out_a = out_override;
+        else {
+            RFV_TRY(ensure_grad(st.srcs[0]));
+            a.out_a = st.srcs[0]->grad;
+            if (st.srcs.size() > 1) { RFV_TRY(ensure_grad(st.srcs[1])); a.out_b = st.srcs[1]->grad; }
+        }
+        a.HW = st.HW; a.slab_shift = slab_shift; a.silu = st.silu ? 1 : 0; a.eps = 1e-5f;
+        const int C = st.C, vpp = C / 8, threads = (256 / vpp) * vpp;
+        a.pix_per_block = std::min(st.HW, std::max(1, 32768 / C));
+        const bool drop = st.drop;
+        const int id = st.id, ig = st.ig, ib = st.ib;
+        ActP sa = st.srcs[0], sb = st.srcs.size() > 1 ? st.srcs[1] : nullptr;
+        const bool over = out_override != nullptr;
+        auto fill = [=](GnBwdArgs& q, const RunCtx& rc) {
+            q.dgamma = gslot(ig); q.dbeta = gslot(ib);
+            q.acc_a = (!over && ka != sa->consumers - 1) ? 1 : 0;
+            q.acc_b = (sb && kb != sb->consumers - 1) ? 1 : 0;
+            q.drop_thresh = drop ? rc.drop_thresh : 0u;
+            q.seed = rc.seed ^ ((uint32_t)id * 0x9E3779B9u);
+            q.drop_scale = rc.drop_scale;
+        };
+        push("gn_bwd", "bwd:gn_reduce:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+            GnBwdArgs q = a;
+            fill(q, rc);
+            dim3 grid((q.HW + q.pix_per_block - 1) / q.pix_per_block, rc.B);
+            gn_bwd_kernel<false><<<grid, threads, 2 * C * sizeof(float), s>>>(q);
+            return cudaGetLastError();
+        });
+        push("gn_bwd", "bwd:gn_apply:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+            GnBwdArgs q = a;
+            fill(q, rc);
+            dim3 grid((q.HW + q.pix_per_block - 1) / q.pix_per_block, rc.B);
+            gn_bwd_kernel<true><<<grid, threads, 0, s>>>(q);
+            return cudaGetLastError();
+        });
         return 0;
     }
 
     int build();
+    int finish_training_setup();
+    int run_backward(const RunCtx& rc, cudaStream_t s);
     int run_forward(const RunCtx& rc, cudaStream_t s);
 };
 
@@ -607,6 +860,39 @@ int rfv_engine::build() {
         stats_floats = (size_t)cap * 16 * mmax * (4 * nlev * nres + 2 * nlev + 8);
     }
     RFV_TRY(dalloc(&stats_arena, stats_floats));
+    if (train) {
+        if (mc > 128) return fail(RFV_ERR_INVALID, "training supports model_channels 64 or 128 (got %d)", mc);
+        int cmax = 0;
+        size_t need = 0;  // largest per-image backward temporary (elements)
+        for (int lv = 0; lv < nlev; ++lv) {
+            const size_t hw = (size_t)(S >> lv) * (S >> lv);
+            const int cin_max = chans[lv] + (lv + 1 < nlev ? chans[lv + 1] : chans[lv]);  // decoder concat [h | skip]
+            need = std::max(need, hw * cin_max);
+            if (lv > 0) need = std::max(need, hw * 4 * chans[lv]);                        // upsampled tensor of level lv at level lv-1
+            cmax = std::max(cmax, cin_max);
+        }
+        need = std::max(need, (size_t)(S >> (nlev - 1)) * (S >> (nlev - 1)) * 3 * chans[nlev - 1]);  // d(qkv)
+        cmax = std::max(cmax, 3 * chans[nlev - 1]);
+        scratch_elems = need;
+        for (int i = 0; i < 3; ++i) RFV_TRY(dalloc(&scratch[i], (size_t)cap * scratch_elems));
+        // one [cap][C][2] slice per norm site: 2 per block (C_in + C_out <= 2 * cmax), attention, output
+        cs_floats = (size_t)cap * 2 * ((size_t)(2 * nlev * nres + 2) * 2 * cmax + 2 * cmax);
+        RFV_TRY(dalloc(&cs_arena, cs_floats));
+        RFV_TRY(dalloc(&d_tproj, (size_t)cap * sumC));
+        RFV_TRY(dalloc(&temb_emb, (size_t)cap * mc));
+        RFV_TRY(dalloc(&temb_z1, (size_t)cap * td));
+        RFV_TRY(dalloc(&temb_h1, (size_t)cap * td));
+        RFV_TRY(dalloc(&temb_z2, (size_t)cap * td));
+        RFV_TRY(dalloc(&d_tz2, (size_t)cap * td));
+        RFV_TRY(dalloc(&d_tz1, (size_t)cap * td));
+        RFV_TRY(dalloc(&dv_buf, (size_t)cap * cfg.out_channels * S * S));
+        const int nlow = (S >> (nlev - 1)) * (S >> (nlev - 1));
+        RFV_TRY(dalloc(&lse, (size_t)cap * cfg.num_heads * nlow));
+        RFV_TRY(dalloc(&delta, (size_t)cap * cfg.num_heads * nlow));
+        RFV_TRY(dalloc(&zero_bias, (size_t)std::max(cmax, 1024)));
+        CU_CHECK(cudaMemset(zero_bias, 0, (size_t)std::max(cmax, 1024) * sizeof(float)));
+        RFV_TRY(dalloc(&norm2, 1));
+    }
 
     // ---- time embedding (models/unet.py:157-162,231) ----
     int tw1, tb1, tw2, tb2;
@@ -619,7 +905,9 @@ int rfv_engine::build() {
         const int td_ = td, mc_ = mc, sumC_ = sumC;
         push("temb", "temb:time_mlp", 2.0 * (mc * td + td * td), [=](const RunCtx& rc, cudaStream_t s) {
             const int rows = rc.t ? rc.B : 1;
-            temb_kernel<<<rows, 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_);
+            float *se = rc.train ? temb_emb : nullptr, *s1 = rc.train ? temb_z1 : nullptr, *s2 = rc.train ? temb_z2 : nullptr;
+            temb_kernel<<<rows, 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_, se, s1,
+                                                                        rc.train ? temb_h1 : nullptr, s2);
             return cudaGetLastError();
         });
         push("temb", "temb:block_projections", 2.0 * td * sumC, [=](const RunCtx& rc, cudaStream_t s) {
@@ -628,6 +916,26 @@ int rfv_engine::build() {
             temb_proj_kernel<<<grid, 256, 8 * td_ * sizeof(float), s>>>(act, wc, bc, proj, rows, td_, sumC_);
             return cudaGetLastError();
         });
+        if (train) {
+            // backward of the time MLP: runs last (first block recorded), after every ResidualBlock has added its
+            // d(time projection) rows into d_tproj.  Needs per-row t (training always passes a t vector).
+            begin_bwd();
+            push("temb_bwd", "bwd:temb", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                const int B = rc.B;
+                for (auto& tp : time_projs) {  // dW_block = d_tproj[:, off:off+C]^T . temb_act ; biases (+ conv1.bias) = column sums
+                    lin_wgrad_kernel<<<(tp.Cout * td_ + 255) / 256, 256, 0, s>>>(d_tproj + tp.off, sumC_, act, td_, gslot(tp.iw), gslot(tp.ib),
+                                                                                gslot(tp.icb), B, tp.Cout, td_);
+                }
+                // dz2 = (d_tproj . Wcat) * silu'(z2)
+                lin_dgrad_kernel<<<(B * td_ + 255) / 256, 256, 0, s>>>(d_tproj, sumC_, wc, d_tz2, temb_z2, B, sumC_, td_);
+                lin_wgrad_kernel<<<(td_ * td_ + 255) / 256, 256, 0, s>>>(d_tz2, td_, temb_h1, td_, gslot(tw2), gslot(tb2), nullptr, B, td_, td_);
+                // dz1 = (dz2 . W2) * silu'(z1)
+                lin_dgrad_kernel<<<(B * td_ + 255) / 256, 256, 0, s>>>(d_tz2, td_, w2, d_tz1, temb_z1, B, td_, td_);
+                lin_wgrad_kernel<<<(td_ * mc_ + 255) / 256, 256, 0, s>>>(d_tz1, td_, temb_emb, mc_, gslot(tw1), gslot(tb1), nullptr, B, td_, mc_);
+                return cudaGetLastError();
+            });
+            end_bwd();
+        }
     }
 
     // ---- input conv (models/unet.py:165,234) ----
@@ -661,6 +969,21 @@ int rfv_engine::build() {
             return cudaGetLastError();
         });
         named_acts["input_conv"] = h;
+        if (train) {
+            RFV_TRY(ensure_grad(h));
+            if (256 % mc != 0) return fail(RFV_ERR_INVALID, "training: model_channels must divide 256");
+            const size_t sw_smem = ((size_t)256 * (mc + 2) * 2 + 15 & ~(size_t)15) + (size_t)4 * 10 * 34 * sizeof(float);
+            CU_CHECK(cudaFuncSetAttribute(small_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
+            begin_bwd();
+            const bf16* dh = h->grad;
+            const int sms = num_sms;
+            push("small_wgrad", "bwd:wgrad:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+                small_wgrad_kernel<<<2 * sms, 256, sw_smem, s>>>(dh, rc.x, rc.x1, rc.t, gslot(iw), rc.B, S, S, mc, Cin, +1, 0);
+                return cudaGetLastError();
+            });
+            bwd_colsum("input_conv.bias", dh, mc, S * S, nullptr, 0, ib, -1);
+            end_bwd();
+        }
     }
 
     int temb_cursor = 0;
@@ -682,7 +1005,19 @@ int rfv_engine::build() {
             ActP o;
             res /= 2;
             RFV_TRY(new_act(&o, chans[lv], res, res, true));
+            const int kd = h->consumers++;
             RFV_TRY(conv_op(d, h, {}, nullptr, o, -1, true));
+            if (train) {
+                RFV_TRY(ensure_grad(o));
+                RFV_TRY(ensure_grad(h));
+                ConvLayer* gd;
+                RFV_TRY(add_dgrad_layer(&gd, d, 2));
+                begin_bwd();
+                RFV_TRY(bwd_wgrad(d->name, 2, h, o->grad, chans[lv], res, res, d->iw, 9 * chans[lv], 0));
+                bwd_colsum(d->name + ".bias", o->grad, chans[lv], res * res, nullptr, 0, d->ib, -1);
+                RFV_TRY(conv_op(gd, grad_view(o), {}, nullptr, grad_view(h), -1, false, h, kd));
+                end_bwd();
+            }
             release(h);
             h = o;
             named_acts["downsamples." + std::to_string(lv)] = h;
@@ -699,8 +1034,10 @@ int rfv_engine::build() {
         if (C % heads != 0 || (d != 32 && d != 64)) return fail(RFV_ERR_INVALID, "attention head dim %d unsupported (32 or 64)", d);
         if (N % 64 != 0) return fail(RFV_ERR_INVALID, "attention needs H*W %% 64 == 0 at the lowest level (got %d)", N);
         ActP hn, qkv, ao, o2;
+        NormSite na;
+        const int kat = h->consumers++;
         RFV_TRY(new_act(&hn, C, res, res, false));
-        RFV_TRY(gn_op("mid_attn.norm", {h}, hn, false));
+        RFV_TRY(gn_op("mid_attn.norm", {h}, hn, false, false, &na));
         ConvLayer *cq, *cp;
         RFV_TRY(add_conv(&cq, "mid_attn.qkv", C, 3 * C, 1, 1, 0, "", 0, 0));
         RFV_TRY(new_act(&qkv, 3 * C, res, res, false));
@@ -713,8 +1050,9 @@ int rfv_engine::build() {
             const float sl2 = (1.0f / std::sqrt((float)d)) * 1.4426950408889634f;
             push("attention", "attn:mid_attn", 4.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
                 dim3 grid(N / 64, heads, rc.B);
-                if (d == 64) attn_kernel<64><<<grid, 128, 0, s>>>(qp, op, N, C, sl2);
-                else attn_kernel<32><<<grid, 128, 0, s>>>(qp, op, N, C, sl2);
+                float* l = rc.train ? lse : nullptr;
+                if (d == 64) attn_kernel<64><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
+                else attn_kernel<32><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
                 return cudaGetLastError();
             });
         }
@@ -722,6 +1060,42 @@ int rfv_engine::build() {
         RFV_TRY(add_conv(&cp, "mid_attn.proj", C, C, 1, 1, 0, "", 0, 0));
         RFV_TRY(new_act(&o2, C, res, res, true));
         RFV_TRY(conv_op(cp, ao, {}, h, o2, -1, true));
+        if (train) {
+            // ---- backward of the attention block (models/unet.py:79-100 reversed) ----
+            RFV_TRY(ensure_grad(o2));
+            ConvLayer *gp, *gq;
+            RFV_TRY(add_dgrad_layer(&gp, cp, 0));
+            RFV_TRY(add_dgrad_layer(&gq, cq, 0));
+            begin_bwd();
+            ActP T0, T1, T2;
+            RFV_TRY(bwd_wgrad("mid_attn.proj", 1, ao, o2->grad, C, res, res, cp->iw, C, 0));
+            bwd_colsum("mid_attn.proj.bias", o2->grad, C, N, nullptr, 0, cp->ib, -1);
+            RFV_TRY(scratch_act(&T0, 0, C, res, res));
+            RFV_TRY(conv_op(gp, grad_view(o2), {}, nullptr, T0, -1, false));   // d(attention output)
+            RFV_TRY(scratch_act(&T1, 1, 3 * C, res, res));
+            {
+                const bf16 *qp = qkv->p, *op = ao->p, *dop = T0->p;
+                bf16* dq = T1->p;
+                const float sc = 1.0f / std::sqrt((float)d), sl2 = sc * 1.4426950408889634f;
+                push("attention_bwd", "bwd:attn:mid_attn", 10.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
+                    dim3 grid(N / 64, heads, rc.B);
+                    if (d == 64) {
+                        attn_bwd_dq_kernel<64><<<grid, 128, 0, s>>>(qp, op, dop, lse, delta, dq, N, C, sc, sl2);
+                        attn_bwd_dkv_kernel<64><<<grid, 128, 0, s>>>(qp, dop, lse, delta, dq, N, C, sc, sl2);
+                    } else {
+                        attn_bwd_dq_kernel<32><<<grid, 128, 0, s>>>(qp, op, dop, lse, delta, dq, N, C, sc, sl2);
+                        attn_bwd_dkv_kernel<32><<<grid, 128, 0, s>>>(qp, dop, lse, delta, dq, N, C, sc, sl2);
+                    }
+                    return cudaGetLastError();
+                });
+            }
+            RFV_TRY(bwd_wgrad("mid_attn.qkv", 1, hn, T1->p, 3 * C, res, res, cq->iw, C, 0));
+            bwd_colsum("mid_attn.qkv.bias", T1->p, 3 * C, N, nullptr, 0, cq->ib, -1);
+            RFV_TRY(scratch_act(&T2, 2, C, res, res));
+            RFV_TRY(conv_op(gq, T1, {}, nullptr, T2, -1, false));              // d(normalised input)
+            RFV_TRY(bwd_gn("mid_attn.norm", na, T2->p, nullptr, o2->grad, kat, 0));  // + identity path x + h
+            end_bwd();
+        }
         release(ao);
         release(h);
         h = o2;
@@ -754,7 +1128,43 @@ int rfv_engine::build() {
             ActP o;
             res *= 2;
             RFV_TRY(new_act(&o, chans[lv], res, res, true));
+            const int ku = h->consumers++;
             RFV_TRY(conv_op(u, h, {}, nullptr, o, -1, true));
+            if (train) {
+                // backward of nearest-x2 + conv3x3 (models/unet.py:215-218): the weight gradient sees the materialised
+                // upsampled input; the data gradient is the plain 3x3 transposed conv at the high resolution followed
+                // by the adjoint of the upsample (2x2 sum pool)
+                RFV_TRY(ensure_grad(o));
+                RFV_TRY(ensure_grad(h));
+                ConvLayer* gu;
+                RFV_TRY(add_dgrad_layer(&gu, u, 0));
+                begin_bwd();
+                ActP U, T;
+                const int Cc = chans[lv], lo = res / 2;
+                RFV_TRY(scratch_act(&U, 0, Cc, res, res));
+                {
+                    const bf16* src = h->p;
+                    bf16* dst = U->p;
+                    push("elementwise_bwd", "bwd:upsample2x:" + u->name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                        upsample2x_kernel<<<4096, 256, 0, s>>>(src, dst, rc.B, lo, lo, Cc);
+                        return cudaGetLastError();
+                    });
+                }
+                RFV_TRY(bwd_wgrad(u->name, 0, U, o->grad, Cc, res, res, u->iw, 9 * Cc, 0));
+                bwd_colsum(u->name + ".bias", o->grad, Cc, res * res, nullptr, 0, u->ib, -1);
+                RFV_TRY(scratch_act(&T, 1, Cc, res, res));
+                RFV_TRY(conv_op(gu, grad_view(o), {}, nullptr, T, -1, false));
+                {
+                    const bf16* src = T->p;
+                    bf16* dst = h->grad;
+                    ActP hh = h;
+                    push("elementwise_bwd", "bwd:sumpool2x2:" + u->name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                        sumpool2x2_kernel<<<4096, 256, 0, s>>>(src, dst, rc.B, lo, lo, Cc, ku != hh->consumers - 1 ? 1 : 0);
+                        return cudaGetLastError();
+                    });
+                }
+                end_bwd();
+            }
             release(h);
             h = o;
             named_acts["upsamples." + std::to_string(li)] = h;
@@ -763,8 +1173,11 @@ int rfv_engine::build() {
     // ---- output (models/unet.py:223-227,275) fused with the Euler update (models/base_flow.py:170) ----
     {
         ActP a;
+        NormSite no;
+        const int ko = h->consumers++;
+        ActP hin = h;
         RFV_TRY(new_act(&a, h->C, S, S, false));
-        RFV_TRY(gn_op("output_conv.0", {h}, a, true));
+        RFV_TRY(gn_op("output_conv.0", {h}, a, true, false, &no));
         release(h);
         int iw, ib;
         const int C = a->C, Co = cfg.out_channels;
@@ -790,6 +1203,46 @@ int rfv_engine::build() {
             output_conv_kernel<<<grid, 256, smem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.B, rc.mode, rc.dt);
             return cudaGetLastError();
         });
+        if (train) {
+            // backward of the output conv: dv (fp32 NCHW, written by the forward in mode 3) -> weight / bias gradient,
+            // data gradient through the thin-conv kernel on flipped weights, then the GroupNorm backward
+            float* wdg = nullptr;  // [Co*9][C] fp32
+            RFV_TRY(dalloc(&wdg, (size_t)Co * 9 * C));
+            {
+                auto prev = params[iw].repack;
+                params[iw].repack = [this, prev, iw, wdg, Co, C](cudaStream_t s) {
+                    const int rc = prev ? prev(s) : 0;
+                    if (rc) return rc;
+                    pack_output_dgrad_weight_kernel<<<(Co * 9 * C + 255) / 256, 256, 0, s>>>(pf(iw), wdg, Co, C);
+                    return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "output dgrad weight pack failed");
+                };
+            }
+            begin_bwd();
+            ActP T0;
+            RFV_TRY(scratch_act(&T0, 0, C, S, S));
+            const size_t sw_smem = (((size_t)256 * (C + 2) * 2 + 15) & ~(size_t)15) + (size_t)4 * 10 * 34 * sizeof(float);
+            const size_t ic_smem = ((size_t)Co * 9 * C + C + (C / 8) * 2) * sizeof(float);
+            bf16* t0 = T0->p;
+            const int ss = slab_shift;
+            push("small_wgrad", "bwd:wgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+                small_wgrad_kernel<<<2 * sms, 256, sw_smem, s>>>(ap, dv_buf, nullptr, nullptr, gslot(iw), rc.B, S, S, C, Co, -1, 1);
+                nchw_channel_sum_kernel<<<dim3(64, Co), 256, 0, s>>>(dv_buf, gslot(ib), rc.B, Co, S * S);
+                return cudaGetLastError();
+            });
+            push("input_conv", "bwd:dgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+                dim3 grid(S * S / 256, rc.B);
+                switch (Co) {
+                    case 1: input_conv_kernel<1><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
+                    case 2: input_conv_kernel<2><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
+                    case 3: input_conv_kernel<3><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
+                    default: input_conv_kernel<4><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
+                }
+                return cudaGetLastError();
+            });
+            RFV_TRY(bwd_gn("output_conv.0", no, t0, nullptr, nullptr, ko, 0));
+            end_bwd();
+            (void)hin;
+        }
         release(a);
     }
     if (temb_cursor != sumC) return fail(RFV_ERR_STATE, "internal: time-projection layout mismatch (%d vs %d)", temb_cursor, sumC);
@@ -840,6 +1293,71 @@ int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// training: flat buffers, backward driver
+// ---------------------------------------------------------------------------------------------------------
+int rfv_engine::finish_training_setup() {
+    RFV_TRY(dalloc(&gflat, (size_t)gtotal));
+    RFV_TRY(dalloc(&mflat, (size_t)gtotal));
+    RFV_TRY(dalloc(&vflat, (size_t)gtotal));
+    CU_CHECK(cudaMemset(gflat, 0, (size_t)gtotal * sizeof(float)));
+    CU_CHECK(cudaMemset(mflat, 0, (size_t)gtotal * sizeof(float)));
+    CU_CHECK(cudaMemset(vflat, 0, (size_t)gtotal * sizeof(float)));
+    RFV_TRY(dalloc(&d_segs, params.size()));
+    std::vector<int2> blocks;
+    for (size_t i = 0; i < params.size(); ++i)
+        for (int64_t c = 0; c * ADAM_CHUNK < params[i].numel; ++c) blocks.push_back(make_int2((int)i, (int)c));
+    n_adam_blocks = (int)blocks.size();
+    RFV_TRY(dalloc(&d_adam_blocks, blocks.size()));
+    CU_CHECK(cudaMemcpy(d_adam_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    adam_dirty = true;
+    return 0;
+}
+
+static AdamSeg make_seg(const Param& p) {
+    AdamSeg s{};
+    s.goff = p.goff; s.numel = p.numel; s.master = p.f32; s.bound = p.bound;
+    s.O = p.O; s.I = p.I; s.KK = p.KK; s.ld = p.KK * p.I; s.koff = 0;
+    return s;
+}
+
+int rfv_engine::run_backward(const RunCtx& rc, cudaStream_t s) {
+    CU_CHECK(cudaMemsetAsync(cs_arena, 0, cs_used * sizeof(float), s));
+    CU_CHECK(cudaMemsetAsync(d_tproj, 0, (size_t)cap * sumC * sizeof(float), s));
+    for (size_t bi = bwd_blocks.size(); bi-- > 0;) {
+        for (auto& op : bwd_blocks[bi]) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (profiling) {
+                CU_CHECK(cudaEventCreate(&e0));
+                CU_CHECK(cudaEventCreate(&e1));
+                CU_CHECK(cudaEventRecord(e0, s));
+            }
+            cudaError_t e = op.run(rc, s);
+            if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "launch of %s failed: %s", op.label.c_str(), cudaGetErrorString(e));
+            ++launches;
+            if (profiling) {
+                CU_CHECK(cudaEventRecord(e1, s));
+                bwd_prof.push_back({&op, e0, e1});
+            }
+        }
+    }
+    if (profiling) {
+        CU_CHECK(cudaStreamSynchronize(s));
+        for (auto& r : bwd_prof) {
+            float ms = 0.f;
+            CU_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            auto& slot = prof[r.op->kind + " " + r.op->label];
+            slot.first += ms;
+            slot.second += 1;
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        bwd_prof.clear();
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------------
 RFV_EXPORT int rfv_abi_version(void) { return RFV_ABI_VERSION; }
@@ -868,6 +1386,8 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
+    e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
+    if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {
         const int c = (cfg->flags >> 8) & 7;
         if (c == 1 || c == 2 || c == 4) e->cluster = c;
@@ -884,6 +1404,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
         e->encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     RFV_TRY(e->build());
+    if (e->train) RFV_TRY(e->finish_training_setup());
     const size_t xin = (size_t)e->cap * cfg->in_channels * cfg->image_size * cfg->image_size;
     RFV_TRY(e->dalloc(&e->scratch_x, xin));
     RFV_TRY(e->dalloc(&e->xbuf[0], xin));
@@ -1045,6 +1566,107 @@ RFV_EXPORT int rfv_fm_loss(rfv_handle h, const float* x0, const float* x1, const
     return h->leave(s);
 }
 
+// ---- training ---------------------------------------------------------------------------------------------
+RFV_EXPORT int rfv_zero_grad(rfv_handle h, void* stream) {
+    if (!h || !h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    RFV_TRY(h->enter((cudaStream_t)stream));
+    CU_CHECK(cudaMemsetAsync(h->gflat, 0, (size_t)h->gtotal * sizeof(float), (cudaStream_t)stream));
+    return h->leave((cudaStream_t)stream);
+}
+
+RFV_EXPORT int rfv_train_accumulate(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch, float dropout_p,
+                                    uint64_t seed, float* loss_out, void* stream) {
+    if (!h || !x0 || !x1 || !t || !loss_out || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail(RFV_ERR_INVALID, "dropout probability must be in [0,1)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t ie = image_elems(h);
+    RFV_TRY(h->enter(s));
+    CU_CHECK(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
+    int64_t idx = 0;
+    for (int64_t b0 = 0; b0 < batch; b0 += h->cap, ++idx) {
+        RunCtx rc;
+        rc.B = (int)std::min<int64_t>(h->cap, batch - b0);
+        rc.x = x0 + b0 * ie; rc.x1 = x1 + b0 * ie; rc.t = t + b0; rc.mode = 3;
+        rc.tgt_x0 = rc.x; rc.tgt_x1 = rc.x1; rc.mse = loss_out;
+        rc.out = h->dv_buf;
+        rc.dt = (float)(2.0 / ((double)batch * (double)ie));   // d mean((v - target)^2) / dv
+        rc.train = true;
+        rc.drop_thresh = (uint32_t)std::lround((double)dropout_p * 65536.0);
+        rc.drop_scale = rc.drop_thresh ? (float)(1.0 / (1.0 - (double)rc.drop_thresh / 65536.0)) : 1.f;
+        rc.seed = (uint32_t)(seed ^ (seed >> 32)) + (uint32_t)idx * 0x85ebca6bu;
+        RFV_TRY(h->run_forward(rc, s));
+        RFV_TRY(h->run_backward(rc, s));
+    }
+    scale_kernel<<<1, 32, 0, s>>>(loss_out, 1, 1.0f / (float)((double)batch * ie));
+    CU_CHECK(cudaGetLastError());
+    return h->leave(s);
+}
+
+RFV_EXPORT int rfv_grad_buffer(rfv_handle h, float** dev_ptr, int64_t* numel) {
+    if (!h || !dev_ptr || !numel) return fail(RFV_ERR_INVALID, "null argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    *dev_ptr = h->gflat;
+    *numel = h->gtotal;
+    return 0;
+}
+
+RFV_EXPORT int rfv_bind_param(rfv_handle h, const char* name, float* dev_ptr) {
+    if (!h || !name) return fail(RFV_ERR_INVALID, "null argument");
+    auto it = h->param_index.find(name);
+    if (it == h->param_index.end()) return fail(RFV_ERR_INVALID, "unknown tensor '%s'", name);
+    h->params[it->second].bound = dev_ptr;
+    h->adam_dirty = true;
+    return 0;
+}
+
+RFV_EXPORT int rfv_get_grad(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, float scale, void* stream) {
+    if (!h || !name || !dev_ptr) return fail(RFV_ERR_INVALID, "null argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    auto it = h->param_index.find(name);
+    if (it == h->param_index.end()) return fail(RFV_ERR_INVALID, "unknown tensor '%s'", name);
+    const Param& p = h->params[it->second];
+    if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements", name, (long long)p.numel);
+    RFV_TRY(h->enter((cudaStream_t)stream));
+    unpack_grad_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(h->gflat, dev_ptr, make_seg(p), scale);
+    CU_CHECK(cudaGetLastError());
+    return h->leave((cudaStream_t)stream);
+}
+
+RFV_EXPORT int rfv_optimizer_step(rfv_handle h, const rfv_adamw* hp, float* grad_norm_out, void* stream) {
+    if (!h || !hp) return fail(RFV_ERR_INVALID, "null argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    if (hp->step < 1) return fail(RFV_ERR_INVALID, "step must be >= 1 (bias correction)");
+    cudaStream_t s = (cudaStream_t)stream;
+    RFV_TRY(h->enter(s));
+    if (h->adam_dirty) {
+        std::vector<AdamSeg> segs;
+        for (auto& p : h->params) segs.push_back(make_seg(p));
+        CU_CHECK(cudaMemcpyAsync(h->d_segs, segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice, s));
+        CU_CHECK(cudaStreamSynchronize(s));  // `segs` is a host temporary
+        h->adam_dirty = false;
+    }
+    CU_CHECK(cudaMemsetAsync(h->norm2, 0, sizeof(float), s));
+    sumsq_kernel<<<1024, 256, 0, s>>>(h->gflat, (size_t)h->gtotal, hp->grad_scale, h->norm2);
+    CU_CHECK(cudaGetLastError());
+    AdamHyper a;
+    a.lr = hp->lr; a.beta1 = hp->beta1; a.beta2 = hp->beta2; a.eps = hp->eps; a.wd = hp->weight_decay;
+    a.max_norm = hp->max_grad_norm; a.grad_scale = hp->grad_scale;
+    a.bc1 = (float)(1.0 - std::pow((double)hp->beta1, (double)hp->step));
+    a.bc2 = (float)(1.0 - std::pow((double)hp->beta2, (double)hp->step));
+    adamw_kernel<<<h->n_adam_blocks, 256, 0, s>>>(h->d_segs, h->d_adam_blocks, h->gflat, h->mflat, h->vflat, h->norm2, a);
+    CU_CHECK(cudaGetLastError());
+    if (grad_norm_out) {
+        CU_CHECK(cudaMemcpyAsync(grad_norm_out, h->norm2, sizeof(float), cudaMemcpyDeviceToDevice, s));
+        sqrt_kernel<<<1, 32, 0, s>>>(grad_norm_out);
+        CU_CHECK(cudaGetLastError());
+    }
+    for (auto& p : h->params)   // refresh every packed / derived copy from the updated fp32 masters
+        if (p.repack) RFV_TRY(p.repack(s));
+    CU_CHECK(cudaEventRecord(h->ev_weights, s));
+    return h->leave(s);
+}
+
 RFV_EXPORT int64_t rfv_launch_count(rfv_handle h, int reset) {
     if (!h) return 0;
     const int64_t v = h->launches;
@@ -1081,6 +1703,8 @@ RFV_EXPORT int rfv_profile_report(rfv_handle h, char* buf, int buf_len) {
     char line[512];
     std::map<std::string, double> flops;
     for (auto& op : h->ops) flops[op.kind + " " + op.label] = op.flops;
+    for (auto& blk : h->bwd_blocks)
+        for (auto& op : blk) flops[op.kind + " " + op.label] = op.flops;
     for (auto& kv : h->prof) {  // "<kind> <label>\t<total ms>\t<launches>\t<algorithmic FLOPs per image>"
         snprintf(line, sizeof(line), "%s\t%.6f\t%lld\t%.1f\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second,
                  flops[kv.first]);

@@ -1,0 +1,503 @@
+// Backward / optimizer kernels of the reflow training step (models/rectified_flow.py:217-238: loss.backward(),
+// clip_grad_norm_, AdamW.step) other than the tensor-core GEMMs (conv dgrad = the forward conv kernels on transposed
+// weights, conv wgrad = wgrad.cuh, attention = attn.cuh).  Everything here is HBM- or latency-bound.
+#pragma once
+#include "common.cuh"
+
+namespace rfv {
+
+// Counter-based dropout mask: one 32-bit hash covers two consecutive elements (16 bits each); an element is KEPT when
+// its 16 bits are >= thresh (thresh = round(p * 65536)).  The backward pass regenerates the mask from the same
+// (seed, element index) instead of storing it.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ void dropout_mask8(uint32_t seed, uint32_t elem0, uint32_t thresh, float scale, float* m) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t h = mix32(seed ^ (((elem0 >> 1) + k) * 0x9E3779B1u));
+        m[2 * k] = (h & 0xFFFFu) >= thresh ? scale : 0.f;
+        m[2 * k + 1] = (h >> 16) >= thresh ? scale : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm(8)(+SiLU)(+dropout) backward over a virtual concat of up to two NHWC bf16 tensors (models/unet.py:56,62,82,224).
+//   y = drop(silu(z)),  z = gamma * xhat + beta,  xhat = (x - mean) * rstd
+//   dz = dy * mask * silu'(z);  dbeta = sum dz;  dgamma = sum dz * xhat
+//   dx = rstd * (gamma * dz - S1/m - xhat * S2/m),  S1 = sum_group gamma*dz,  S2 = sum_group gamma*dz*xhat,  m = group size
+// Pass 1 (reduce): per-(image, channel) sums A = sum_pix dz, B = sum_pix dz*xhat into cs[n][c][2].  S1, S2, dgamma,
+// dbeta all derive from them.  Pass 2 (apply): dx, plus up to two addends (the block's identity / shortcut path),
+// written (or accumulated) into the gradient tensors of the two sources.
+// Thread mapping as gn_apply_kernel: a thread owns one 8-channel vector position for the whole block.
+// ---------------------------------------------------------------------------------------------------------
+struct GnBwdArgs {
+    const bf16* dy;            // [B][HW][C] gradient w.r.t. the GroupNorm(+SiLU) output (C = Ca + Cb)
+    const bf16* xa; const bf16* xb;
+    const float* stats_a; const float* stats_b;
+    const float* gamma; const float* beta;
+    float* cs;                 // [B][C][2]
+    const bf16* add_cat;       // [B][HW][C]  optional addend in concat layout
+    const bf16* add_a;         // [B][HW][Ca] optional addend for source a
+    bf16* out_a; bf16* out_b;  // gradient tensors of the sources
+    float* dgamma; float* dbeta;
+    int acc_a, acc_b;          // accumulate into out_a / out_b instead of overwriting
+    int Ca, Cb, HW, slab_shift, silu, pix_per_block;
+    float eps;
+    uint32_t drop_thresh, seed; float drop_scale;
+};
+
+__device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, int g, int cpg, float* mean, float* rstd) {
+    const int slab = 1 << a.slab_shift;
+    float s = 0.f, ss = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; c += slab) {
+        const float* src = (c < a.Ca) ? a.stats_a + ((size_t)n * (a.Ca >> a.slab_shift) + (c >> a.slab_shift)) * 2
+                                      : a.stats_b + ((size_t)n * (a.Cb >> a.slab_shift) + ((c - a.Ca) >> a.slab_shift)) * 2;
+        s += src[0];
+        ss += src[1];
+    }
+    const float cnt = (float)cpg * (float)a.HW;
+    const float m = s / cnt;
+    *mean = m;
+    *rstd = rsqrtf(fmaxf(ss / cnt - m * m, 0.f) + a.eps);
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdArgs a) {
+    extern __shared__ float sm[];   // reduce: [2*C] partial sums
+    __shared__ float gmean[8], grstd[8], gS1[8], gS2[8];
+    const int C = a.Ca + a.Cb, n = blockIdx.y, cpg = C / 8;
+    if (threadIdx.x < 8) {
+        const int g = threadIdx.x;
+        gn_group_stats(a, n, g, cpg, &gmean[g], &grstd[g]);
+        if (APPLY) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float gm = a.gamma[c];
+                s1 += gm * a.cs[((size_t)n * C + c) * 2];
+                s2 += gm * a.cs[((size_t)n * C + c) * 2 + 1];
+            }
+            const float inv = 1.0f / ((float)cpg * (float)a.HW);
+            gS1[g] = s1 * inv;
+            gS2[g] = s2 * inv;
+        }
+    }
+    if (!APPLY)
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    if (APPLY && blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(a.dbeta + c, a.cs[((size_t)n * C + c) * 2]);
+            atomicAdd(a.dgamma + c, a.cs[((size_t)n * C + c) * 2 + 1]);
+        }
+    __syncthreads();
+    const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
+    const int grp = (cv * 8) / cpg;
+    const float mean = gmean[grp], rstd = grstd[grp];
+    float gam[8], bet[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gam[j] = a.gamma[cv * 8 + j]; bet[j] = a.beta[cv * 8 + j]; }
+    const bool from_a = cv * 8 < a.Ca;
+    const bf16* src = from_a ? a.xa + cv * 8 : a.xb + (cv * 8 - a.Ca);
+    const int cs_ = from_a ? a.Ca : a.Cb;
+    bf16* dst = from_a ? a.out_a + cv * 8 : a.out_b + (cv * 8 - a.Ca);
+    const bool acc = from_a ? a.acc_a != 0 : a.acc_b != 0;
+    const int p0 = blockIdx.x * a.pix_per_block;
+    const int np = min(a.pix_per_block, a.HW - p0);
+    const size_t base = (size_t)n * a.HW + p0;
+    float accA[8], accB[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+    const float s1 = APPLY ? gS1[grp] : 0.f, s2 = APPLY ? gS2[grp] : 0.f;
+    for (int pp = pl; pp < np; pp += pstride) {
+        const uint4 qx = *reinterpret_cast<const uint4*>(src + (base + pp) * cs_);
+        const uint4 qd = *reinterpret_cast<const uint4*>(a.dy + (base + pp) * C + cv * 8);
+        float x[8], d[8], mk[8];
+        unpack8(qx, x);
+        unpack8(qd, d);
+        if (a.drop_thresh) dropout_mask8(a.seed, (uint32_t)((base + pp) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (x[j] - mean) * rstd;
+            float dz = a.drop_thresh ? d[j] * mk[j] : d[j];
+            if (a.silu) {
+                const float z = fmaf(gam[j], xh, bet[j]);
+                const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+                dz *= sg * (1.0f + z * (1.0f - sg));
+            }
+            if (APPLY) r[j] = rstd * (gam[j] * dz - s1 - xh * s2);
+            else { accA[j] += dz; accB[j] += dz * xh; }
+        }
+        if (APPLY) {
+            if (a.add_cat) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(a.add_cat + (base + pp) * C + cv * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] += f[j];
+            }
+            if (a.add_a && from_a) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(a.add_a + (base + pp) * a.Ca + cv * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] += f[j];
+            }
+            uint4* o = reinterpret_cast<uint4*>(dst + (base + pp) * cs_);
+            if (acc) {
+                float f[8];
+                unpack8(*o, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] += f[j];
+            }
+            *o = pack8(r);
+        }
+    }
+    if (!APPLY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sm[(cv * 8 + j) * 2], accA[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], accB[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.cs + (size_t)n * C * 2 + i, sm[i]);
+    }
+}
+
+// Per-(image, channel) and per-channel sums of an NHWC bf16 tensor: conv-bias gradients and the gradient of the
+// per-block time projection (models/unet.py:59-60 adds it to every pixel).  grid (pixel chunks, B).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out_nc, int ld_nc,
+                                                     float* __restrict__ out_c1, float* __restrict__ out_c2, int C, int HW,
+                                                     int pix_per_block) {
+    extern __shared__ float sm[];  // [C]
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
+    const int p0 = blockIdx.x * pix_per_block, np = min(pix_per_block, HW - p0);
+    const size_t base = (size_t)n * HW + p0;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (threadIdx.x < pstride * vpp)
+        for (int pp = pl; pp < np; pp += pstride) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(dy + (base + pp) * C + cv * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    if (threadIdx.x < pstride * vpp) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = sm[c];
+        if (out_nc) atomicAdd(out_nc + (size_t)n * ld_nc + c, v);
+        if (out_c1) atomicAdd(out_c1 + c, v);
+        if (out_c2) atomicAdd(out_c2 + c, v);
+    }
+}
+
+// Nearest x2 upsample of an NHWC bf16 tensor (materialised only for the upsample conv's weight gradient).
+__global__ void upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+    const int vpp = C >> 3;
+    const size_t total = (size_t)B * 4 * H * W * vpp;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % vpp);
+        size_t r = idx / vpp;
+        const int ow = (int)(r % (2 * W)); r /= (2 * W);
+        const int oh = (int)(r % (2 * H));
+        const int n = (int)(r / (2 * H));
+        reinterpret_cast<uint4*>(out)[idx] = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + (oh >> 1)) * W + (ow >> 1)) * C + cv * 8);
+    }
+}
+// 2x2 sum pool (the adjoint of the nearest upsample): out[n,i,j,:] (+)= sum of the four children.
+__global__ void sumpool2x2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int accumulate) {
+    const int vpp = C >> 3;
+    const size_t total = (size_t)B * H * W * vpp;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % vpp);
+        size_t r = idx / vpp;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(in + (((size_t)n * 2 * H + 2 * h + a) * 2 * W + 2 * w + b) * C + cv * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += f[j];
+            }
+        uint4* o = reinterpret_cast<uint4*>(out) + idx;
+        if (accumulate) {
+            float f[8];
+            unpack8(*o, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += f[j];
+        }
+        *o = pack8(s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient of the two thin convolutions (input conv 3->64, output conv 64->3; models/unet.py:165,226):
+//   acc[c][s][tap] = sum_{n,pix} big[n,pix,c] * small[n,s,pix + sgn*off(tap)]
+// big: NHWC bf16 with Cb (<= 64) channels; small: NCHW fp32 with Cs (<= 4) channels, optionally the interpolation
+// (1-t) x0 + t x1 formed on the fly.  sgn=+1, out[(c*Cs+s)*9+tap]: input conv (big = dY, small = x_t);
+// sgn=-1, out[(s*Cb+c)*9+tap]: output conv (big = activations, small = dv).
+// Persistent blocks walk 8x32-pixel tiles, accumulate in registers and flush once with atomics.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) small_wgrad_kernel(const bf16* __restrict__ big, const float* __restrict__ sm0,
+                                                          const float* __restrict__ sm1, const float* __restrict__ tvec,
+                                                          float* __restrict__ out, int B, int H, int W, int Cb, int Cs, int sgn,
+                                                          int out_mode) {
+    constexpr int TH = 8, TW = 32;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    bf16* bt = reinterpret_cast<bf16*>(smraw);                               // [256][Cb+2]
+    const int bld = Cb + 2;
+    float* st = reinterpret_cast<float*>(smraw + ((256 * bld * 2 + 15) & ~15));  // [Cs][TH+2][TW+2]
+    const int tw = (W + TW - 1) / TW, th = (H + TH - 1) / TH, ntiles = tw * th * B;
+    const int tid = threadIdx.x;
+    const int c = tid % Cb, grp = tid / Cb, ngrp = 256 / Cb;   // Cb divides 256 (64)
+    const int ncombo = Cs * 9;
+    const int per = (ncombo + ngrp - 1) / ngrp;                // <= 9 with Cb = 64, Cs <= 4
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / (tw * th), r = tile - n * (tw * th);
+        const int h0 = (r / tw) * TH, w0 = (r % tw) * TW;
+        const float tb = sm1 ? tvec[n] : 0.f;
+        __syncthreads();
+        for (int i = tid; i < Cs * (TH + 2) * (TW + 2); i += 256) {
+            const int s = i / ((TH + 2) * (TW + 2)), rr = i % ((TH + 2) * (TW + 2));
+            const int hh = h0 + rr / (TW + 2) - 1, ww = w0 + rr % (TW + 2) - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const size_t o = (((size_t)n * Cs + s) * H + hh) * W + ww;
+                v = sm0[o];
+                if (sm1) v = (1.0f - tb) * v + tb * sm1[o];
+            }
+            st[i] = v;
+        }
+        for (int i = tid; i < 256 * (Cb / 8); i += 256) {
+            const int p = i / (Cb / 8), cv = i % (Cb / 8);
+            const int hh = h0 + p / TW, ww = w0 + p % TW;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (hh < H && ww < W) q = *reinterpret_cast<const uint4*>(big + (((size_t)n * H + hh) * W + ww) * Cb + cv * 8);
+            uint32_t* d = reinterpret_cast<uint32_t*>(bt + p * bld + cv * 8);
+            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+        }
+        __syncthreads();
+        if (grp < ngrp) {
+            for (int p = 0; p < 256; ++p) {
+                const float v = __bfloat162float(bt[p * bld + c]);
+                const int ph = p / TW, pw = p % TW;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int combo = grp * per + k;
+                    if (k < per && combo < ncombo) {
+                        const int s = combo / 9, tap = combo % 9;
+                        const int dy = sgn * (tap / 3 - 1), dx = sgn * (tap % 3 - 1);
+                        acc[k] = fmaf(v, st[(s * (TH + 2) + ph + 1 + dy) * (TW + 2) + pw + 1 + dx], acc[k]);
+                    }
+                }
+            }
+        }
+    }
+    if (grp < ngrp) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int combo = grp * per + k;
+            if (k < per && combo < ncombo) {
+                const int s = combo / 9, tap = combo % 9;
+                const size_t o = out_mode == 0 ? ((size_t)c * Cs + s) * 9 + tap : ((size_t)s * Cb + c) * 9 + tap;
+                atomicAdd(out + o, acc[k]);
+            }
+        }
+    }
+}
+
+// Per-channel sums of an NCHW fp32 tensor with few channels (output-conv bias gradient).
+__global__ void nchw_channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int HW) {
+    __shared__ float red[8];
+    const int c = blockIdx.y;
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)B * HW; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = i / HW, p = i - n * HW;
+        s += x[(n * C + c) * HW + p];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        atomicAdd(out + c, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Small dense layers of the time MLP (models/unet.py:157-162 and ResidualBlock.time_mlp :43-46), fp32.
+// ---------------------------------------------------------------------------------------------------------
+// dW[o][i] += sum_b dy[b*ldy + o] * x[b*ldx + i];  db[o] += sum_b dy[b*ldy + o]
+__global__ void lin_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, float* __restrict__ dW,
+                                 float* __restrict__ db, float* __restrict__ db2, int rows, int O, int I) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= O * I) return;
+    const int o = idx / I, i = idx - o * I;
+    float s = 0.f, sb = 0.f;
+    for (int b = 0; b < rows; ++b) {
+        const float d = dy[(size_t)b * ldy + o];
+        s = fmaf(d, x[(size_t)b * ldx + i], s);
+        sb += d;
+    }
+    dW[idx] += s;
+    if (i == 0) {
+        if (db) db[o] += sb;
+        if (db2) db2[o] += sb;
+    }
+}
+// dx[b][i] = sum_o dy[b*ldy + o] * W[o][i]   (optionally * silu'(z[b][i]))
+__global__ void lin_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ Wt, float* __restrict__ dx,
+                                 const float* __restrict__ z, int rows, int O, int I) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * I) return;
+    const int b = idx / I, i = idx - b * I;
+    float s = 0.f;
+    for (int o = 0; o < O; ++o) s = fmaf(dy[(size_t)b * ldy + o], Wt[(size_t)o * I + i], s);
+    if (z) {
+        const float zz = z[idx];
+        const float sg = 1.0f / (1.0f + __expf(-zz));
+        s *= sg * (1.0f + zz * (1.0f - sg));
+    }
+    dx[idx] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight layouts of the data-gradient convolutions (the forward kernels run on these)
+// ---------------------------------------------------------------------------------------------------------
+// OIHW fp32 [O][I][KK] -> bf16 [I][KK*O]:  dst[i][t*O + o] = src[o][i][KK-1-t]  (transposed, spatially flipped)
+__global__ void pack_conv_weight_T_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int KK, int i_total, int i_off) {
+    const size_t total = (size_t)O * I * KK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / ((size_t)I * KK));
+        const int r = (int)(idx - (size_t)o * I * KK);
+        const int i = r / KK, tap = r - i * KK;
+        (void)i_total;
+        dst[((size_t)(i_off + i) * KK + (KK - 1 - tap)) * O + o] = __float2bfloat16_rn(src[idx]);
+    }
+}
+// Data gradient of a 3x3 stride-2 pad-1 conv as four sub-pixel phases of 2x2 taps over dY (the layout the
+// sub-pixel upsample kernel consumes): dst[(phase*I + i)][(a*2+b)*O + o], rows (py,a) -> ky: (0,1)->1 (1,0)->2 (1,1)->0.
+__global__ void pack_down_dgrad_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
+    const size_t total = (size_t)16 * O * I;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx % O);
+        const int tap = (int)((idx / O) % 4);
+        const int i = (int)((idx / ((size_t)4 * O)) % I);
+        const int phase = (int)(idx / ((size_t)4 * O * I));
+        const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+        const int ky = py == 0 ? (a == 1 ? 1 : -1) : (a == 0 ? 2 : 0);
+        const int kx = px == 0 ? (b == 1 ? 1 : -1) : (b == 0 ? 2 : 0);
+        const float v = (ky >= 0 && kx >= 0) ? src[((size_t)o * I + i) * 9 + ky * 3 + kx] : 0.f;
+        dst[idx] = __float2bfloat16_rn(v);
+    }
+}
+// Output conv data gradient in the shape input_conv_kernel consumes: wt[(s*9 + t)][c] = W[s][c][8-t], fp32.
+__global__ void pack_output_dgrad_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Co * 9 * C) {
+        const int c = i % C, t = (i / C) % 9, s = i / (9 * C);
+        dst[i] = src[((size_t)s * C + c) * 9 + (8 - t)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Global-norm clipping + AdamW (torch.nn.utils.clip_grad_norm_(params, 1.0); torch.optim.AdamW defaults)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float scale, float* __restrict__ out) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = g[i] * scale;
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        atomicAdd(out, t);
+    }
+}
+
+struct AdamSeg {      // one parameter tensor
+    long long goff;   // offset of its slot in the flat gradient / moment buffers
+    long long numel;
+    float* master;    // engine fp32 copy (reference layout)
+    float* bound;     // caller's parameter storage (torch), or null
+    int O, I, KK;     // conv weight: slot layout [O][KK][I] vs reference [O][I][KK]; KK == 0: identical layouts
+    int ld;           // slot row length (floats) -- rows of a packed conv gradient may be longer than KK*I
+    int koff;         // column of this tensor inside the slot row
+    int no_decay;     // unused (torch AdamW decays every parameter)
+};
+struct AdamHyper { float lr, beta1, beta2, eps, wd, max_norm, grad_scale, bc1, bc2; };
+
+constexpr int ADAM_CHUNK = 4096;
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamSeg* __restrict__ segs, const int2* __restrict__ blocks,
+                                                    const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ norm2, AdamHyper h) {
+    const int2 bk = blocks[blockIdx.x];
+    const AdamSeg s = segs[bk.x];
+    float clip = 1.0f;
+    if (h.max_norm > 0.f) {
+        const float tn = sqrtf(*norm2);
+        clip = fminf(1.0f, h.max_norm / (tn + 1e-6f));
+    }
+    const float gs = h.grad_scale * clip;
+    const long long j0 = (long long)bk.y * ADAM_CHUNK;
+    for (long long j = j0 + threadIdx.x; j < j0 + ADAM_CHUNK && j < s.numel; j += blockDim.x) {
+        long long gi, ri;   // gradient-slot index, reference-layout index
+        if (s.KK > 0) {     // j enumerates the slot order [o][tap][i]
+            const int o = (int)(j / ((long long)s.KK * s.I));
+            const int r = (int)(j - (long long)o * s.KK * s.I);
+            const int tap = r / s.I, i = r - tap * s.I;
+            gi = s.goff + (long long)o * s.ld + s.koff + r;
+            ri = ((long long)o * s.I + i) * s.KK + tap;
+        } else { gi = s.goff + j; ri = j; }
+        const float gr = g[gi] * gs;
+        const float mm = h.beta1 * m[gi] + (1.0f - h.beta1) * gr;
+        const float vv = h.beta2 * v[gi] + (1.0f - h.beta2) * gr * gr;
+        m[gi] = mm;
+        v[gi] = vv;
+        float p = s.master[ri];
+        p *= (1.0f - h.lr * h.wd);
+        p -= h.lr * (mm / h.bc1) / (sqrtf(vv / h.bc2) + h.eps);
+        s.master[ri] = p;
+        if (s.bound) s.bound[ri] = p;
+    }
+}
+__global__ void sqrt_kernel(float* v) { if (threadIdx.x == 0) *v = sqrtf(*v); }
+// Gradient slot -> reference layout (tests / rfv_get_grad).
+__global__ void unpack_grad_kernel(const float* __restrict__ g, float* __restrict__ dst, AdamSeg s, float scale) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < s.numel; j += (long long)gridDim.x * blockDim.x) {
+        long long gi, ri;
+        if (s.KK > 0) {
+            const int o = (int)(j / ((long long)s.KK * s.I));
+            const int r = (int)(j - (long long)o * s.KK * s.I);
+            const int tap = r / s.I, i = r - tap * s.I;
+            gi = s.goff + (long long)o * s.ld + s.koff + r;
+            ri = ((long long)o * s.I + i) * s.KK + tap;
+        } else { gi = s.goff + j; ri = j; }
+        dst[ri] = g[gi] * scale;
+    }
+}
+
+}  // namespace rfv

@@ -18,6 +18,8 @@ from . import _build
 RFV_MAX_LEVELS = 8
 FLAG_NO_UMMA = 1
 FLAG_NO_GRAPH = 2
+FLAG_KEEP_ACTS = 4
+FLAG_TRAIN = 32
 
 
 class RfvConfig(C.Structure):
@@ -26,6 +28,20 @@ class RfvConfig(C.Structure):
                 ("channel_mult", C.c_int32 * RFV_MAX_LEVELS), ("num_res_blocks", C.c_int32),
                 ("num_heads", C.c_int32), ("micro_batch", C.c_int32), ("device", C.c_int32),
                 ("flags", C.c_int32)]
+
+
+class RfvAdamW(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float),
+                ("step", C.c_int64)]
+
+
+class _DeviceArray:
+    """Exposes engine-owned device memory to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, numel: int):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2,
+                                         "strides": None}
 
 
 # every symbol include/rfv.h declares: (restype, argtypes)
@@ -44,6 +60,12 @@ SYMBOLS = {
     "rfv_euler_sample_host": (C.c_int, [_VP, _FP, _FP, _I64, C.c_int]),
     "rfv_straightness": (C.c_int, [_VP, _FP, _FP, _I64, C.c_int, _FP, _VP]),
     "rfv_fm_loss": (C.c_int, [_VP, _FP, _FP, _FP, _I64, _FP, _VP]),
+    "rfv_zero_grad": (C.c_int, [_VP, _VP]),
+    "rfv_train_accumulate": (C.c_int, [_VP, _FP, _FP, _FP, _I64, C.c_float, C.c_uint64, _FP, _VP]),
+    "rfv_grad_buffer": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_I64)]),
+    "rfv_get_grad": (C.c_int, [_VP, C.c_char_p, _FP, _I64, C.c_float, _VP]),
+    "rfv_bind_param": (C.c_int, [_VP, C.c_char_p, _FP]),
+    "rfv_optimizer_step": (C.c_int, [_VP, C.POINTER(RfvAdamW), _FP, _VP]),
     "rfv_launch_count": (_I64, [_VP, C.c_int]),
     "rfv_flops_per_image": (C.c_double, [_VP]),
     "rfv_debug_activation": (_I64, [_VP, C.c_char_p, _FP, _I64, _VP]),
@@ -99,7 +121,7 @@ class Engine:
     """One native handle: architecture + resolution + device.  Owns packed weights and the activation arena."""
 
     def __init__(self, arch: Dict, image_size: int, device: torch.device, micro_batch: Optional[int] = None,
-                 flags: Optional[int] = None):
+                 flags: Optional[int] = None, train: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: rectified_flow_vision_b200 runs only on sm_100a GPUs")
         self.lib = load_library()
@@ -124,6 +146,9 @@ class Engine:
         cfg.micro_batch = micro_batch or default_micro_batch(image_size)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         cfg.flags = int(os.environ.get("RFV_FLAGS", "0")) if flags is None else flags
+        if train:
+            cfg.flags |= FLAG_TRAIN
+        self.train = bool(cfg.flags & FLAG_TRAIN)
         self.micro_batch = cfg.micro_batch
         h = _VP()
         with torch.cuda.device(self.device):
@@ -166,7 +191,8 @@ class Engine:
             for full, numel in self.tensor_names:
                 key = full[len(prefix):] if full.startswith(prefix) else full
                 p = params[key]
-                tag = (p.data_ptr(), p._version)
+                # _weights_gen: bumped when a native optimizer step rewrote the storage behind torch's back
+                tag = (p.data_ptr(), p._version, getattr(unet, "_weights_gen", 0))
                 if self._versions.get(full) == tag:
                     continue
                 src = p.detach()
@@ -235,6 +261,73 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_fm_loss(self.h, x0.data_ptr(), x1.data_ptr(), t.data_ptr(), x0.shape[0],
                                         out.data_ptr(), self._stream()))
+        return out
+
+    # ----- training (needs train=True) --------------------------------------------------------------------
+    def zero_grad(self) -> None:
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_zero_grad(self.h, self._stream()))
+
+    def train_accumulate(self, x0: torch.Tensor, x1: torch.Tensor, t: torch.Tensor, dropout_p: float = 0.0,
+                         seed: int = 0) -> torch.Tensor:
+        """loss = mean((v((1-t) x0 + t x1, t) - (x1 - x0))^2); parameter gradients are ADDED to the flat
+        gradient buffer.  Returns the loss as a 0-dim device tensor (no host sync)."""
+        x0 = self._dev_f32(x0, "x0")
+        x1 = self._dev_f32(x1, "x1")
+        t = self._dev_f32(t, "t")
+        if x0.shape != x1.shape or t.shape[0] != x0.shape[0]:
+            raise ValueError(f"shape mismatch: x0 {tuple(x0.shape)}, x1 {tuple(x1.shape)}, t {tuple(t.shape)}")
+        out = torch.empty((), dtype=torch.float32, device=x0.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_train_accumulate(self.h, x0.data_ptr(), x1.data_ptr(), t.data_ptr(), x0.shape[0],
+                                                 float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(),
+                                                 self._stream()))
+        return out
+
+    def grad_buffer(self) -> torch.Tensor:
+        """The engine's flat fp32 gradient buffer as a torch tensor sharing its memory (all-reduce target)."""
+        ptr, n = _VP(), _I64()
+        _check(self.lib.rfv_grad_buffer(self.h, C.byref(ptr), C.byref(n)))
+        return torch.as_tensor(_DeviceArray(ptr.value, n.value), device=self.device)
+
+    def get_grad(self, name: str, numel: int, scale: float = 1.0) -> torch.Tensor:
+        out = torch.empty(numel, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_get_grad(self.h, name.encode(), out.data_ptr(), numel, float(scale), self._stream()))
+        return out
+
+    def bind_params(self, unet: torch.nn.Module, prefix: str = "velocity_net.") -> None:
+        """The optimizer step then also writes the updated fp32 values into the module's own parameter storage, so
+        ``state_dict()`` / ``save()`` always see the trained weights."""
+        self.sync_weights(unet, prefix)
+        params = dict(unet.named_parameters())
+        self._bound = []
+        self._bound_module, self._bound_prefix = unet, prefix
+        for full, numel in self.tensor_names:
+            key = full[len(prefix):] if full.startswith(prefix) else full
+            p = params[key]
+            if p.device != self.device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise ValueError(f"{full}: parameters must be contiguous fp32 tensors on {self.device} to be trained")
+            _check(self.lib.rfv_bind_param(self.h, full.encode(), p.data_ptr()))
+            self._bound.append(p)
+
+    def optimizer_step(self, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                       weight_decay: float = 0.01, max_grad_norm: float = 1.0, grad_scale: float = 1.0) -> torch.Tensor:
+        """clip_grad_norm_(max_grad_norm) + torch.optim.AdamW step; returns the pre-clip gradient norm (device)."""
+        hp = RfvAdamW(lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, int(step))
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_optimizer_step(self.h, C.byref(hp), out.data_ptr(), self._stream()))
+        # the bound parameter storage was rewritten behind torch's back: other engines of the module must re-upload,
+        # this one already holds the new values
+        unet = getattr(self, "_bound_module", None)
+        if unet is not None:
+            unet._weights_gen = getattr(unet, "_weights_gen", 0) + 1
+            params = dict(unet.named_parameters())
+            for full, _ in self.tensor_names:
+                key = full[len(self._bound_prefix):] if full.startswith(self._bound_prefix) else full
+                p = params[key]
+                self._versions[full] = (p.data_ptr(), p._version, unet._weights_gen)
         return out
 
     # ----- introspection ---------------------------------------------------------------------------------

@@ -69,10 +69,33 @@ def generate_reflow_pairs(teacher_model: BaseFlowModel, num_pairs: int, batch_si
 def train_rectified_flow(model: RectifiedFlowModel, x0_data: torch.Tensor, x1_data: torch.Tensor,
                          epochs: int = 30, batch_size: int = 16, lr: float = 1e-4,
                          save_path: Optional[str] = None, save_every: int = 10) -> List[float]:
-    """models/rectified_flow.py:177-255.  Needs the native backward + AdamW step."""
-    raise NotImplementedError(
-        "train_rectified_flow: the native backward/optimizer step is not implemented yet; this package does "
-        "not fall back to PyTorch autograd.")
+    """models/rectified_flow.py:177-255 with the step body (interpolation, forward, MSE, backward, clip, AdamW) run by
+    the native engine: same shuffled TensorDataset/DataLoader batching, t ~ U[0,1) drawn on the device per batch,
+    torch.optim.AdamW(lr) defaults, CosineAnnealingLR(epochs) stepped per epoch, checkpoints every ``save_every``."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from .training import NativeTrainer, cosine_lr
+
+    dataset = TensorDataset(x0_data, x1_data)
+    dataloader = DataLoader(dataset, batch_size=batch_size, shuffle=True)
+    trainer = NativeTrainer(model, lr=lr)
+    losses: List[float] = []
+    for epoch in range(epochs):
+        model.train()
+        cur_lr = cosine_lr(lr, epoch, epochs)
+        epoch_losses = []
+        for x0, x1 in dataloader:
+            x0 = x0.to(model.device)
+            x1 = x1.to(model.device)
+            t = torch.rand(x0.shape[0], device=model.device)
+            epoch_losses.append(trainer.step(x0, x1, t, lr=cur_lr))
+        avg_loss = float(torch.stack(epoch_losses).mean().item())  # one host sync per epoch, not per step
+        losses.append(avg_loss)
+        print(f"Reflow Epoch {epoch+1}/{epochs} - Loss: {avg_loss:.4f}")
+        if save_path and (epoch + 1) % save_every == 0:
+            model.save(f"{save_path}_epoch{epoch+1}.pt")
+    if save_path:
+        model.save(f"{save_path}_final.pt")
+    return losses
 
 
 def iterative_reflow(initial_model: BaseFlowModel, real_data_loader, num_iterations: int = 2,

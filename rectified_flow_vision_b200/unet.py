@@ -127,6 +127,7 @@ class UNet(_Node):
                 node.weight = nn.Parameter(w)
                 node.bias = nn.Parameter(b)
         self._engine = None
+        self._train_engine = None
 
     # ----- engine plumbing ------------------------------------------------------------------------------
     def arch(self) -> Dict:
@@ -148,6 +149,23 @@ class UNet(_Node):
             eng = _engine.Engine(self.arch(), image_size, dev)
             self._engine = eng
         eng.sync_weights(self)
+        return eng
+
+    def train_engine(self, image_size: int, device, micro_batch=None) -> "_engine.Engine":
+        """Handle with the backward plan (RFV_FLAG_TRAIN); the optimizer writes through to this module's parameters."""
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"rectified_flow_vision_b200 trains only on sm_100a GPUs (got device {dev}); no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        eng = self._train_engine
+        if eng is None or eng.image_size != image_size or eng.device != dev:
+            mb = micro_batch or max(8, (128 * 64 * 64) // (image_size * image_size))
+            eng = _engine.Engine(self.arch(), image_size, dev, micro_batch=mb, train=True)
+            eng.bind_params(self)
+            self._train_engine = eng
+        else:
+            eng.sync_weights(self)
         return eng
 
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:

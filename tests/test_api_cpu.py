@@ -80,7 +80,7 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 32, 32), torch.zeros(1))
     with pytest.raises(RuntimeError):
         m.sample(batch_size=1, num_steps=1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):   # the trainer is native too: no autograd fallback
         pkg.train_rectified_flow(m, torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32), epochs=1)
 
 

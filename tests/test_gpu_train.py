@@ -1,0 +1,140 @@
+"""GPU parity of the native TRAINING STEP (rfv_train_accumulate + rfv_optimizer_step through the C ABI) against the
+reference's own step (tests/golden/train_*.npz) and the CPU oracle (oracle/train_oracle.py).
+
+Tolerances (bf16 activations AND bf16 activation gradients, fp32 accumulation, fp32 parameter gradients / Adam):
+  loss                       relative 5e-3   (measured 4e-5)
+  total gradient norm        relative 1e-2   (measured 1e-3)
+  per-tensor gradient        rel-L2 <= 5e-2 for every tensor with a non-negligible gradient (measured <= 2.2e-2)
+  per-tensor gradient norm   relative 5e-2   (measured 4e-3)
+  3-step loss trajectory     relative 5e-2 per step (Adam's sign-like update amplifies gradient noise where |g| ~ 0)
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOSS, TOL_GNORM, TOL_GRAD_L2, TOL_TRAJ = 5e-3, 1e-2, 5e-2, 5e-2
+
+
+@pytest.fixture(scope="module", params=["small32", "default64"])
+def case(request):
+    return request.param
+
+
+def _setup(case):
+    import rectified_flow_vision_b200 as pkg
+    m = util.seeded_model(case, device="cuda:0", cls=pkg.RectifiedFlowModel)
+    g = util.golden(case)
+    x0, x1, t = (torch.from_numpy(g[k]).cuda() for k in ("x", "x1", "t"))
+    return m, x0, x1, t, np.load(f"{util.GOLD}/train_{case}.npz")
+
+
+def test_gradients_vs_reference(case):
+    m, x0, x1, t, tg = _setup(case)
+    eng = m.velocity_net.train_engine(x0.shape[-1], "cuda:0", micro_batch=4)
+    eng.zero_grad()
+    loss = float(eng.train_accumulate(x0, x1, t, dropout_p=0.0, seed=1).item())
+    assert abs(loss - tg["losses"][0]) <= TOL_LOSS * tg["losses"][0], loss
+    names = [str(n) for n in tg["names"]]
+    sd = dict(m.named_parameters())
+    gn = []
+    worst = (0.0, "")
+    for k in names:
+        g = eng.get_grad(k, sd[k].numel()).cpu().numpy()
+        assert np.isfinite(g).all(), k
+        gn.append(float(np.sqrt((g.astype(np.float64) ** 2).sum())))
+        for pre, sl in (("grad_full/", slice(None)), ("grad_sampled/", slice(None, None, int(tg["stride"])))):
+            if pre + k in tg.files:
+                ref = tg[pre + k].reshape(-1)
+                err = util.rel_l2(g.reshape(-1)[sl], ref)
+                worst = max(worst, (err, k))
+                assert err <= TOL_GRAD_L2, (k, err)
+    gn, ref = np.array(gn), tg["grad_norm_per_tensor"]
+    total, total_ref = float(np.sqrt((gn ** 2).sum())), float(np.sqrt((ref ** 2).sum()))
+    assert abs(total - total_ref) <= TOL_GNORM * total_ref, (total, total_ref)
+    big = ref > 1e-3 * ref.max()
+    rel = np.abs(gn - ref)[big] / ref[big]
+    assert rel.max() <= TOL_GRAD_L2, (names[int(np.flatnonzero(big)[rel.argmax()])], float(rel.max()))
+    print(f"{case}: loss {loss:.5f} (ref {tg['losses'][0]:.5f}); |g| {total:.4f} (ref {total_ref:.4f}); "
+          f"worst tensor rel-L2 {worst[0]:.3e} at {worst[1]}; worst norm rel {rel.max():.3e}")
+
+
+def test_gradients_vs_oracle_on_fresh_inputs(case):
+    """Same check against the CPU oracle on inputs the goldens do not cover (different batch size and seed)."""
+    from oracle import train_oracle as T
+    m, x0, _, _, _ = _setup(case)
+    gen = torch.Generator().manual_seed(7)
+    B, C, S = 5, x0.shape[1], x0.shape[-1]
+    a, b, t = torch.randn(B, C, S, S, generator=gen), torch.randn(B, C, S, S, generator=gen), torch.rand(B, generator=gen)
+    kw = util.manifest()["cases"][case]["kwargs"]
+    arch = dict(model_channels=kw.get("model_channels", 64), channel_mult=tuple(kw.get("channel_mult", [1, 2, 4])),
+                num_res_blocks=kw.get("num_res_blocks", 2))
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    loss_ref, grads = T.loss_and_grads(P, a, b, t, **arch)
+    eng = m.velocity_net.train_engine(S, "cuda:0", micro_batch=4)   # 5 rows in micro-batches of 4 + 1: accumulation
+    eng.zero_grad()
+    loss = float(eng.train_accumulate(a.cuda(), b.cuda(), t.cuda(), dropout_p=0.0, seed=3).item())
+    assert abs(loss - loss_ref) <= TOL_LOSS * loss_ref
+    gmax = max(float(g.norm()) for g in grads.values())
+    for k, gr in grads.items():
+        if float(gr.norm()) < 1e-3 * gmax:
+            continue
+        g = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape)
+        assert util.rel_l2(g, gr.numpy()) <= TOL_GRAD_L2, (k, util.rel_l2(g, gr.numpy()))
+
+
+def test_three_optimizer_steps_vs_reference(case):
+    from rectified_flow_vision_b200.training import NativeTrainer
+    m, x0, x1, t, tg = _setup(case)
+    m.eval()  # dropout off, like the golden run
+    p0 = {k: v.detach().clone() for k, v in m.named_parameters()}
+    tr = NativeTrainer(m, lr=float(tg["lr"]), micro_batch=4)
+    losses, norms = [], []
+    for _ in range(len(tg["losses"])):
+        losses.append(float(tr.step(x0, x1, t).item()))
+        norms.append(float(tr.last_grad_norm.item()))
+    np.testing.assert_allclose(losses, tg["losses"], rtol=TOL_TRAJ)
+    np.testing.assert_allclose(norms, tg["grad_norms_total"], rtol=2 * TOL_TRAJ)
+    # the optimizer wrote through to the torch parameters: state_dict() now holds the trained weights
+    names = [str(n) for n in tg["names"]]
+    sd = dict(m.named_parameters())
+    upd = np.array([float((sd[k].detach() - p0[k]).norm()) for k in names])
+    ref = tg["update_norm"]
+    assert (upd > 0).all()
+    big = ref > 1e-2 * ref.max()
+    assert (np.abs(upd - ref)[big] / ref[big]).max() <= 0.15
+    # and the sampling engine sees them too (weight generation bump): eval forward differs from the initial model
+    v = m(x0, t)
+    assert torch.isfinite(v).all()
+
+
+def test_dropout_mask_is_consistent_and_unbiased():
+    """Training-mode dropout (p = 0.1, models/unet.py:62): deterministic per seed, different across seeds, and the
+    loss stays close to the p = 0 loss (inverted-dropout scaling keeps activations unbiased)."""
+    m, x0, x1, t, tg = _setup("small32")
+    eng = m.velocity_net.train_engine(x0.shape[-1], "cuda:0", micro_batch=4)
+    vals = []
+    for seed in (11, 11, 12):
+        eng.zero_grad()
+        vals.append(float(eng.train_accumulate(x0, x1, t, dropout_p=0.1, seed=seed).item()))
+    assert vals[0] == vals[1] or abs(vals[0] - vals[1]) < 1e-4 * vals[0]   # atomics reorder the last bits only
+    assert vals[0] != vals[2]
+    assert abs(vals[0] - tg["losses"][0]) < 0.1 * tg["losses"][0]
+    g = eng.get_grad("velocity_net.output_conv.2.bias", 3)
+    assert torch.isfinite(g).all()
+
+
+def test_train_rectified_flow_api_reduces_loss():
+    """The public trainer (models/rectified_flow.py:177-255 signature) on a tiny synthetic reflow problem."""
+    import rectified_flow_vision_b200 as pkg
+    torch.manual_seed(0)
+    m = pkg.RectifiedFlowModel(image_size=32, channel_mult=[1, 2], num_res_blocks=1, device="cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    x0 = torch.randn(64, 3, 32, 32, generator=gen)
+    x1 = 0.5 * x0 + 0.25                                   # a learnable linear coupling
+    losses = pkg.train_rectified_flow(m, x0, x1, epochs=4, batch_size=16, lr=1e-3)
+    assert len(losses) == 4 and all(np.isfinite(losses))
+    assert losses[-1] < 0.6 * losses[0], losses
