@@ -114,6 +114,30 @@ def cpu_port_pairs_per_sec(sample_images: int, sample_steps: int, repeats: int =
     return img_steps_per_s / EULER_STEPS, cores, best
 
 
+def cpu_train_images_per_sec(batch: int):
+    import torch
+    from oracle import train_oracle
+    import rectified_flow_vision_b200 as pkg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = pkg.BaseFlowModel(device="cpu")
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    x0, x1, t = torch.randn(batch, CH, IMAGE, IMAGE, generator=g), torch.randn(batch, CH, IMAGE, IMAGE, generator=g), torch.rand(batch, generator=g)
+    state = {}
+    best = None
+    for step in range(3):  # first step is the warm-up
+        t0 = time.perf_counter()
+        _, grads = train_oracle.loss_and_grads(P, x0, x1, t)
+        train_oracle.adamw_step(P, grads, state, step + 1)
+        dt = time.perf_counter() - t0
+        if step > 0:
+            best = dt if best is None else min(best, dt)
+    return {"value": batch / best, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"one optimizer step at batch {batch} ({best:.2f} s): oracle/train_oracle.py (autograd over the fp32 port + restated clip/AdamW)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -225,6 +249,41 @@ def run_ours(args):
     e2e_value = world * P * e2e_steps / e2e_s
     img_bytes = P * CH * IMAGE * IMAGE * 4
 
+    # ---- reflow training step (BASELINE.json configs[3]): fwd + bwd + clip + AdamW on synthetic pairs, data parallel:
+    #      per-GPU batch fixed (weak scaling), ONE all-reduce of the flat fp32 gradient buffer per step over NCCL ----
+    train = None
+    if not args.no_train:
+        from rectified_flow_vision_b200.training import NativeTrainer
+        tb = args.train_batch
+        tmodel = pkg.RectifiedFlowModel(device=f"cuda:{local}")   # same seed on every rank: identical replicas
+        tmodel.train()
+        tr = NativeTrainer(tmodel, lr=1e-4, micro_batch=min(tb, 256))
+        tg = torch.Generator().manual_seed(1000 + rank)
+        tx0 = torch.randn(tb, CH, IMAGE, IMAGE, generator=tg).to(dev)
+        tx1 = torch.randn(tb, CH, IMAGE, IMAGE, generator=tg).to(dev)
+        tt = torch.rand(tb, generator=tg).to(dev)
+        for _ in range(3):
+            tr.step(tx0, tx1, tt)
+        barrier()
+        teng = tmodel.velocity_net.train_engine(IMAGE, dev)
+        teng.launch_count(reset=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = 5
+        a.record()
+        for _ in range(tsteps):
+            loss = tr.step(tx0, tx1, tt)
+        b.record()
+        barrier()
+        tms = max_over_ranks(a.elapsed_time(b)) / tsteps
+        train = {"images_per_sec": world * tb / (tms / 1e3), "ms_per_step": tms, "batch_per_gpu": tb, "dropout": 0.1,
+                 "loss": float(loss.item()), "grad_allreduce_bytes": int(teng.grad_buffer().numel() * 4) if world > 1 else 0,
+                 "gpu_launches_per_step": int(teng.launch_count(reset=True)) // tsteps,
+                 "tflops_at_3x_forward": world * tb * 3 * FLOPS_PER_IMG_STEP / (tms / 1e3) / 1e12,
+                 "what": "train_rectified_flow step body: x_t interpolation, UNet fwd, MSE, bwd, clip_grad_norm_(1.0), AdamW; "
+                         "synthetic N(0,1) pairs, t ~ U[0,1), seeded; gradients all-reduced (SUM) then scaled 1/world"}
+        del tr, tmodel, teng
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -241,6 +300,8 @@ def run_ours(args):
                 "achieved_tflops": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world,
                 "of_sustained": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["sustained"],
                 "of_burst": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["burst"], "peaks": pk["source"]}}
+    if train is not None:
+        line["train_step"] = train
 
     if world == 1:
         # ---- per-kernel-class split + roofline of the dominant kernel, measured live with CUDA events ----
@@ -263,15 +324,23 @@ def run_ours(args):
         for k in kinds.values():
             k["share"] = k["ms"] / tot_ms
         line["kernel_split_ms_per_forward"] = {"micro_batch": mb, **{k: v for k, v in kinds.items()}}
-        if "conv_umma" in kinds:
-            # algorithmic FLOPs (2*MACs, rfv_profile_report) of the convolutions the tcgen05 kernel executed
-            fl = kinds["conv_umma"]["gflop_per_image"] * 1e9 * mb
-            secs = kinds["conv_umma"]["ms"] / 1e3
-            ach = fl / secs / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_umma_kernel<BN> (tcgen05 implicit-GEMM convs, all launches of one forward)",
+        tc = {k: kinds[k] for k in ("conv_halo", "conv_umma") if k in kinds}
+        if tc:
+            # dominant kernel = the tcgen05 conv class with the most time in a forward; algorithmic FLOPs (2*MACs,
+            # rfv_profile_report) of the convolutions it executed / CUDA-event time of its launches
+            names = {"conv_halo": "conv_halo_kernel<BN> (tcgen05 3x3 convs with halo reuse, all launches of one forward)",
+                     "conv_umma": "conv_umma_kernel<BN> (tcgen05 implicit-GEMM convs, all launches of one forward)"}
+            dom = max(tc, key=lambda k: tc[k]["ms"])
+            fl = tc[dom]["gflop_per_image"] * 1e9 * mb
+            ach = fl / (tc[dom]["ms"] / 1e3) / 1e12
+            fl_all = sum(v["gflop_per_image"] for v in tc.values()) * 1e9 * mb
+            ach_all = fl_all / (sum(v["ms"] for v in tc.values()) / 1e3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": names[dom],
                                 "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
                                 "frac_of_burst": ach / pk["burst"], "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                                "traffic": None, "flops_per_forward": fl, "ms_per_forward": kinds["conv_umma"]["ms"]}
+                                "traffic": None, "flops_per_forward": fl, "ms_per_forward": tc[dom]["ms"],
+                                "all_tcgen05_convs": {"achieved": ach_all, "frac": ach_all / pk["sustained"],
+                                                      "frac_of_burst": ach_all / pk["burst"]}}
         # ---- sampling throughput, configs[0] (B=64) and configs[2] (B=4096) ----
         samp = {}
         for bsz, reps in ((64, 5), (4096, 2)):
@@ -297,6 +366,11 @@ def run_ours(args):
                                               "functional-PyTorch fp32 port of the reference path (oracle/torch_port.py)"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)}
+        if train is not None:
+            try:   # the training step of the oracle (autograd over the functional port + restated AdamW) on the host cores
+                train["cpu_baseline"] = cpu_train_images_per_sec(8)
+            except Exception as ex:  # noqa: BLE001
+                train["cpu_baseline"] = {"value": None, "error": str(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -309,6 +383,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=512)
+    ap.add_argument("--train-batch", type=int, default=256, help="per-GPU batch of the training-step measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

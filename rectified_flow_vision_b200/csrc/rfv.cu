@@ -659,9 +659,8 @@ struct rfv_engine {
             RFV_TRY(scratch_act(&Ta2, 1, Cout, H, W));
             RFV_TRY(conv_op(g2, dOut, {}, nullptr, Ta2, -1, false));
             RFV_TRY(scratch_act(&Th, 2, Cout, H, W));
-            RFV_TRY(bwd_gn(name + ".norm2", n2, Ta2->p, nullptr, nullptr, 0, 0, Th->p));
-            // d(time projection)[n][c] = sum over pixels of dh; conv1.bias and time_mlp.1.bias get its batch sum later
-            bwd_colsum(name + ".time", Th->p, Cout, H * W, d_tproj + off, sumC, -1, -1);
+            // also d(time projection)[n][c] = sum over pixels of dh (conv1.bias and time_mlp.1.bias get its batch sum later)
+            RFV_TRY(bwd_gn(name + ".norm2", n2, Ta2->p, nullptr, nullptr, 0, 0, Th->p, d_tproj + off, sumC));
             RFV_TRY(bwd_wgrad(name + ".conv1", 0, a1, Th->p, Cout, W, H, c1->iw, 9 * Cin, 0));
             RFV_TRY(scratch_act(&Ta1, 1, Cin, H, W));
             RFV_TRY(conv_op(g1, Th, {}, nullptr, Ta1, -1, false));
@@ -776,7 +775,7 @@ struct rfv_engine {
     // ka / kb: consumer index this norm's block holds on srcs[0] / srcs[1]; out_override: write the (single-source)
     // result there instead of srcs[0]->grad (intermediate tensors that have no gradient buffer of their own).
     int bwd_gn(const std::string& label, const NormSite& st, const bf16* dy, const bf16* add_cat, const bf16* add_a, int ka, int kb,
-               bf16* out_override = nullptr) {
+               bf16* out_override = nullptr, float* out_colsum = nullptr, int ld_colsum = 0) {
         GnBwdArgs a{};
         a.dy = dy;
         a.xa = st.srcs[0]->p; a.stats_a = st.srcs[0]->stats; a.Ca = st.srcs[0]->C;
@@ -791,8 +790,9 @@ struct rfv_engine {
             if (st.srcs.size() > 1) { RFV_TRY(ensure_grad(st.srcs[1])); a.out_b = st.srcs[1]->grad; }
         }
         a.HW = st.HW; a.slab_shift = slab_shift; a.silu = st.silu ? 1 : 0; a.eps = 1e-5f;
+        a.out_colsum = out_colsum; a.ld_colsum = ld_colsum;
         const int C = st.C, vpp = C / 8, threads = (256 / vpp) * vpp;
-        a.pix_per_block = std::min(st.HW, std::max(1, 32768 / C));
+        a.pix_per_block = std::min(st.HW, std::max(1, 65536 / C));
         const bool drop = st.drop;
         const int id = st.id, ig = st.ig, ib = st.ib;
         ActP sa = st.srcs[0], sb = st.srcs.size() > 1 ? st.srcs[1] : nullptr;
@@ -816,7 +816,7 @@ struct rfv_engine {
             GnBwdArgs q = a;
             fill(q, rc);
             dim3 grid((q.HW + q.pix_per_block - 1) / q.pix_per_block, rc.B);
-            gn_bwd_kernel<true><<<grid, threads, 0, s>>>(q);
+            gn_bwd_kernel<true><<<grid, threads, q.out_colsum ? C * sizeof(float) : 0, s>>>(q);
             return cudaGetLastError();
         });
         return 0;
@@ -861,7 +861,7 @@ int rfv_engine::build() {
     }
     RFV_TRY(dalloc(&stats_arena, stats_floats));
     if (train) {
-        if (mc > 128) return fail(RFV_ERR_INVALID, "training supports model_channels 64 or 128 (got %d)", mc);
+        if (mc != 64) return fail(RFV_ERR_INVALID, "training supports model_channels == 64 (got %d)", mc);
         int cmax = 0;
         size_t need = 0;  // largest per-image backward temporary (elements)
         for (int lv = 0; lv < nlev; ++lv) {
@@ -922,16 +922,21 @@ int rfv_engine::build() {
             begin_bwd();
             push("temb_bwd", "bwd:temb", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
                 const int B = rc.B;
-                for (auto& tp : time_projs) {  // dW_block = d_tproj[:, off:off+C]^T . temb_act ; biases (+ conv1.bias) = column sums
-                    lin_wgrad_kernel<<<(tp.Cout * td_ + 255) / 256, 256, 0, s>>>(d_tproj + tp.off, sumC_, act, td_, gslot(tp.iw), gslot(tp.ib),
-                                                                                gslot(tp.icb), B, tp.Cout, td_);
-                }
+                // dW_block = d_tproj[:, off:off+C]^T . temb_act ; biases (+ conv1.bias) = column sums: all blocks in one launch
+                LinSegs sg{};
+                if ((int)time_projs.size() > LIN_MAX_SEGS) return cudaErrorInvalidValue;
+                for (auto& tp : time_projs) sg.s[sg.n++] = LinSeg{tp.off, tp.Cout, gslot(tp.iw), gslot(tp.ib), gslot(tp.icb)};
+                lin_wgrad_kernel<<<(sumC_ * td_ + 255) / 256, 256, 0, s>>>(d_tproj, sumC_, act, td_, sg, B, sumC_, td_);
                 // dz2 = (d_tproj . Wcat) * silu'(z2)
                 lin_dgrad_kernel<<<(B * td_ + 255) / 256, 256, 0, s>>>(d_tproj, sumC_, wc, d_tz2, temb_z2, B, sumC_, td_);
-                lin_wgrad_kernel<<<(td_ * td_ + 255) / 256, 256, 0, s>>>(d_tz2, td_, temb_h1, td_, gslot(tw2), gslot(tb2), nullptr, B, td_, td_);
+                LinSegs s2{};
+                s2.n = 1; s2.s[0] = LinSeg{0, td_, gslot(tw2), gslot(tb2), nullptr};
+                lin_wgrad_kernel<<<(td_ * td_ + 255) / 256, 256, 0, s>>>(d_tz2, td_, temb_h1, td_, s2, B, td_, td_);
                 // dz1 = (dz2 . W2) * silu'(z1)
                 lin_dgrad_kernel<<<(B * td_ + 255) / 256, 256, 0, s>>>(d_tz2, td_, w2, d_tz1, temb_z1, B, td_, td_);
-                lin_wgrad_kernel<<<(td_ * mc_ + 255) / 256, 256, 0, s>>>(d_tz1, td_, temb_emb, mc_, gslot(tw1), gslot(tb1), nullptr, B, td_, mc_);
+                LinSegs s1{};
+                s1.n = 1; s1.s[0] = LinSeg{0, td_, gslot(tw1), gslot(tb1), nullptr};
+                lin_wgrad_kernel<<<(td_ * mc_ + 255) / 256, 256, 0, s>>>(d_tz1, td_, temb_emb, mc_, s1, B, td_, mc_);
                 return cudaGetLastError();
             });
             end_bwd();
@@ -971,7 +976,7 @@ int rfv_engine::build() {
         named_acts["input_conv"] = h;
         if (train) {
             RFV_TRY(ensure_grad(h));
-            if (256 % mc != 0) return fail(RFV_ERR_INVALID, "training: model_channels must divide 256");
+            if (mc != 64) return fail(RFV_ERR_INVALID, "training: the thin-conv weight-gradient kernel is sized for model_channels == 64 (got %d)", mc);
             const size_t sw_smem = ((size_t)256 * (mc + 2) * 2 + 15 & ~(size_t)15) + (size_t)4 * 10 * 34 * sizeof(float);
             CU_CHECK(cudaFuncSetAttribute(small_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
             begin_bwd();

@@ -42,6 +42,8 @@ struct GnBwdArgs {
     const bf16* add_a;         // [B][HW][Ca] optional addend for source a
     bf16* out_a; bf16* out_b;  // gradient tensors of the sources
     float* dgamma; float* dbeta;
+    float* out_colsum;         // optional [B][ld_colsum]: per-(image, channel) sums of the produced gradient (source a only)
+    int ld_colsum;
     int acc_a, acc_b;          // accumulate into out_a / out_b instead of overwriting
     int Ca, Cb, HW, slab_shift, silu, pix_per_block;
     float eps;
@@ -64,7 +66,7 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, int g,
 }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     extern __shared__ float sm[];   // reduce: [2*C] partial sums
     __shared__ float gmean[8], grstd[8], gS1[8], gS2[8];
     const int C = a.Ca + a.Cb, n = blockIdx.y, cpg = C / 8;
@@ -109,47 +111,65 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
     const float s1 = APPLY ? gS1[grp] : 0.f, s2 = APPLY ? gS2[grp] : 0.f;
-    for (int pp = pl; pp < np; pp += pstride) {
-        const uint4 qx = *reinterpret_cast<const uint4*>(src + (base + pp) * cs_);
-        const uint4 qd = *reinterpret_cast<const uint4*>(a.dy + (base + pp) * C + cv * 8);
-        float x[8], d[8], mk[8];
-        unpack8(qx, x);
-        unpack8(qd, d);
-        if (a.drop_thresh) dropout_mask8(a.seed, (uint32_t)((base + pp) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
-        float r[8];
+    const bool has_cat = APPLY && a.add_cat != nullptr, has_a = APPLY && a.add_a != nullptr && from_a;
+    constexpr int U = 2;
+    for (int pp = pl; pp < np; pp += U * pstride) {
+        uint4 qx[U], qd[U], qc[U], qa[U], qo[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (x[j] - mean) * rstd;
-            float dz = a.drop_thresh ? d[j] * mk[j] : d[j];
-            if (a.silu) {
-                const float z = fmaf(gam[j], xh, bet[j]);
-                const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
-                dz *= sg * (1.0f + z * (1.0f - sg));
+        for (int u = 0; u < U; ++u) {   // all loads of the batch first (memory-level parallelism)
+            const int px = pp + u * pstride;
+            if (px < np) {
+                qx[u] = *reinterpret_cast<const uint4*>(src + (base + px) * cs_);
+                qd[u] = *reinterpret_cast<const uint4*>(a.dy + (base + px) * C + cv * 8);
+                if (has_cat) qc[u] = *reinterpret_cast<const uint4*>(a.add_cat + (base + px) * C + cv * 8);
+                if (has_a) qa[u] = *reinterpret_cast<const uint4*>(a.add_a + (base + px) * a.Ca + cv * 8);
+                if (APPLY && acc) qo[u] = *reinterpret_cast<const uint4*>(dst + (base + px) * cs_);
             }
-            if (APPLY) r[j] = rstd * (gam[j] * dz - s1 - xh * s2);
-            else { accA[j] += dz; accB[j] += dz * xh; }
         }
-        if (APPLY) {
-            if (a.add_cat) {
-                float f[8];
-                unpack8(*reinterpret_cast<const uint4*>(a.add_cat + (base + pp) * C + cv * 8), f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] += f[j];
-            }
-            if (a.add_a && from_a) {
-                float f[8];
-                unpack8(*reinterpret_cast<const uint4*>(a.add_a + (base + pp) * a.Ca + cv * 8), f);
+        for (int u = 0; u < U; ++u) {
+            const int px = pp + u * pstride;
+            if (px >= np) continue;
+            float x[8], d[8], mk[8];
+            unpack8(qx[u], x);
+            unpack8(qd[u], d);
+            if (a.drop_thresh) dropout_mask8(a.seed, (uint32_t)((base + px) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
+            float r[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] += f[j];
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (x[j] - mean) * rstd;
+                float dz = a.drop_thresh ? d[j] * mk[j] : d[j];
+                if (a.silu) {
+                    const float z = fmaf(gam[j], xh, bet[j]);
+                    const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+                    dz *= sg * (1.0f + z * (1.0f - sg));
+                }
+                if (APPLY) r[j] = rstd * (gam[j] * dz - s1 - xh * s2);
+                else { accA[j] += dz; accB[j] += dz * xh; }
             }
-            uint4* o = reinterpret_cast<uint4*>(dst + (base + pp) * cs_);
-            if (acc) {
+            if (APPLY) {
                 float f[8];
-                unpack8(*o, f);
+                if (has_cat) {
+                    unpack8(qc[u], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] += f[j];
+                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                }
+                if (has_a) {
+                    unpack8(qa[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                }
+                if (acc) {
+                    unpack8(qo[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                }
+                if (a.out_colsum) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) accA[j] += r[j];
+                }
+                *reinterpret_cast<uint4*>(dst + (base + px) * cs_) = pack8(r);
             }
-            *o = pack8(r);
         }
     }
     if (!APPLY) {
@@ -160,6 +180,13 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdArgs a) {
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.cs + (size_t)n * C * 2 + i, sm[i]);
+    } else if (a.out_colsum) {   // dynamic shared memory [C] (the launcher sizes it)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], accA[j]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.Ca; i += blockDim.x) atomicAdd(a.out_colsum + (size_t)n * a.ld_colsum + i, sm[i]);
     }
 }
 
@@ -178,13 +205,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (threadIdx.x < pstride * vpp)
-        for (int pp = pl; pp < np; pp += pstride) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(dy + (base + pp) * C + cv * 8), f);
+    constexpr int U = 8;
+    for (int pp = pl; pp < np; pp += U * pstride) {
+        uint4 q[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += f[j];
-        }
+        for (int u = 0; u < U; ++u)
+            if (pp + u * pstride < np) q[u] = *reinterpret_cast<const uint4*>(dy + (base + pp + u * pstride) * C + cv * 8);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (pp + u * pstride < np) {
+                float f[8];
+                unpack8(q[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+    }
     if (threadIdx.x < pstride * vpp) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], acc[j]);
@@ -256,27 +291,39 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const bf16* __restrict
                                                           const float* __restrict__ sm1, const float* __restrict__ tvec,
                                                           float* __restrict__ out, int B, int H, int W, int Cb, int Cs, int sgn,
                                                           int out_mode) {
-    constexpr int TH = 8, TW = 32;
+    // thread = (channel PAIR cp, combo group grp): one 32-bit shared load brings two channels of a pixel, each
+    // small-tensor value is reused for both; offsets of the thread's (s, tap) combos are precomputed.
+    constexpr int TH = 8, TW = 32, SW = TW + 2, MAXK = 8;
     extern __shared__ __align__(16) uint8_t smraw[];
     bf16* bt = reinterpret_cast<bf16*>(smraw);                               // [256][Cb+2]
     const int bld = Cb + 2;
     float* st = reinterpret_cast<float*>(smraw + ((256 * bld * 2 + 15) & ~15));  // [Cs][TH+2][TW+2]
     const int tw = (W + TW - 1) / TW, th = (H + TH - 1) / TH, ntiles = tw * th * B;
     const int tid = threadIdx.x;
-    const int c = tid % Cb, grp = tid / Cb, ngrp = 256 / Cb;   // Cb divides 256 (64)
+    const int npair = Cb / 2, ngrp = 256 / npair;              // Cb = 64: 32 pairs x 8 groups
+    const int cp = tid % npair, grp = tid / npair;
     const int ncombo = Cs * 9;
-    const int per = (ncombo + ngrp - 1) / ngrp;                // <= 9 with Cb = 64, Cs <= 4
-    float acc[9];
+    const int per = (ncombo + ngrp - 1) / ngrp;                // <= MAXK (host checks)
+    int off[MAXK];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (int k = 0; k < MAXK; ++k) {
+        const int combo = grp * per + k;
+        if (k < per && combo < ncombo) {
+            const int s = combo / 9, tap = combo % 9;
+            off[k] = (s * (TH + 2) + 1 + sgn * (tap / 3 - 1)) * SW + 1 + sgn * (tap % 3 - 1);
+        } else off[k] = -1;
+    }
+    float acc0[MAXK], acc1[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int n = tile / (tw * th), r = tile - n * (tw * th);
         const int h0 = (r / tw) * TH, w0 = (r % tw) * TW;
         const float tb = sm1 ? tvec[n] : 0.f;
         __syncthreads();
-        for (int i = tid; i < Cs * (TH + 2) * (TW + 2); i += 256) {
-            const int s = i / ((TH + 2) * (TW + 2)), rr = i % ((TH + 2) * (TW + 2));
-            const int hh = h0 + rr / (TW + 2) - 1, ww = w0 + rr % (TW + 2) - 1;
+        for (int i = tid; i < Cs * (TH + 2) * SW; i += 256) {
+            const int s = i / ((TH + 2) * SW), rr = i % ((TH + 2) * SW);
+            const int hh = h0 + rr / SW - 1, ww = w0 + rr % SW - 1;
             float v = 0.f;
             if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
                 const size_t o = (((size_t)n * Cs + s) * H + hh) * W + ww;
@@ -294,30 +341,32 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const bf16* __restrict
             d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
         }
         __syncthreads();
-        if (grp < ngrp) {
-            for (int p = 0; p < 256; ++p) {
-                const float v = __bfloat162float(bt[p * bld + c]);
-                const int ph = p / TW, pw = p % TW;
+        for (int ph = 0; ph < TH; ++ph) {
+#pragma unroll 4
+            for (int pw = 0; pw < TW; ++pw) {
+                const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bt + (ph * TW + pw) * bld + cp * 2));
+                const float* sp = st + ph * SW + pw;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const int combo = grp * per + k;
-                    if (k < per && combo < ncombo) {
-                        const int s = combo / 9, tap = combo % 9;
-                        const int dy = sgn * (tap / 3 - 1), dx = sgn * (tap % 3 - 1);
-                        acc[k] = fmaf(v, st[(s * (TH + 2) + ph + 1 + dy) * (TW + 2) + pw + 1 + dx], acc[k]);
+                for (int k = 0; k < MAXK; ++k)
+                    if (off[k] >= 0) {
+                        const float x = sp[off[k]];
+                        acc0[k] = fmaf(v.x, x, acc0[k]);
+                        acc1[k] = fmaf(v.y, x, acc1[k]);
                     }
-                }
             }
         }
     }
-    if (grp < ngrp) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const int combo = grp * per + k;
-            if (k < per && combo < ncombo) {
-                const int s = combo / 9, tap = combo % 9;
-                const size_t o = out_mode == 0 ? ((size_t)c * Cs + s) * 9 + tap : ((size_t)s * Cb + c) * 9 + tap;
-                atomicAdd(out + o, acc[k]);
+    for (int k = 0; k < MAXK; ++k) {
+        const int combo = grp * per + k;
+        if (off[k] >= 0) {
+            const int s = combo / 9, tap = combo % 9, c = cp * 2;
+            if (out_mode == 0) {
+                atomicAdd(out + ((size_t)c * Cs + s) * 9 + tap, acc0[k]);
+                atomicAdd(out + ((size_t)(c + 1) * Cs + s) * 9 + tap, acc1[k]);
+            } else {
+                atomicAdd(out + ((size_t)s * Cb + c) * 9 + tap, acc0[k]);
+                atomicAdd(out + ((size_t)s * Cb + c + 1) * 9 + tap, acc1[k]);
             }
         }
     }
@@ -345,32 +394,59 @@ __global__ void nchw_channel_sum_kernel(const float* __restrict__ x, float* __re
 // ---------------------------------------------------------------------------------------------------------
 // Small dense layers of the time MLP (models/unet.py:157-162 and ResidualBlock.time_mlp :43-46), fp32.
 // ---------------------------------------------------------------------------------------------------------
-// dW[o][i] += sum_b dy[b*ldy + o] * x[b*ldx + i];  db[o] += sum_b dy[b*ldy + o]
-__global__ void lin_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, float* __restrict__ dW,
-                                 float* __restrict__ db, float* __restrict__ db2, int rows, int O, int I) {
+// dW[o][i] += sum_b dy[b*ldy + o] * x[b*ldx + i];  db[o] += sum_b dy[b*ldy + o].  The output rows may be scattered over
+// several parameter tensors (the per-block time projections): `segs` maps row ranges to destinations.
+struct LinSeg { int row0, rows; float* dW; float* db; float* db2; };
+constexpr int LIN_MAX_SEGS = 48;
+struct LinSegs { int n; LinSeg s[LIN_MAX_SEGS]; };
+__global__ void __launch_bounds__(256) lin_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx,
+                                                        const __grid_constant__ LinSegs segs, int rows, int O, int I) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= O * I) return;
     const int o = idx / I, i = idx - o * I;
-    float s = 0.f, sb = 0.f;
-    for (int b = 0; b < rows; ++b) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, sb = 0.f;
+    int b = 0;
+    for (; b + 4 <= rows; b += 4) {
+        const float d0 = dy[(size_t)b * ldy + o], d1 = dy[(size_t)(b + 1) * ldy + o], d2 = dy[(size_t)(b + 2) * ldy + o],
+                    d3 = dy[(size_t)(b + 3) * ldy + o];
+        const float x0 = x[(size_t)b * ldx + i], x1 = x[(size_t)(b + 1) * ldx + i], x2 = x[(size_t)(b + 2) * ldx + i],
+                    x3 = x[(size_t)(b + 3) * ldx + i];
+        s0 = fmaf(d0, x0, s0); s1 = fmaf(d1, x1, s1); s2 = fmaf(d2, x2, s2); s3 = fmaf(d3, x3, s3);
+        sb += (d0 + d1) + (d2 + d3);
+    }
+    for (; b < rows; ++b) {
         const float d = dy[(size_t)b * ldy + o];
-        s = fmaf(d, x[(size_t)b * ldx + i], s);
+        s0 = fmaf(d, x[(size_t)b * ldx + i], s0);
         sb += d;
     }
-    dW[idx] += s;
+    const float s = (s0 + s1) + (s2 + s3);
+    int k = 0;
+    while (k + 1 < segs.n && o >= segs.s[k].row0 + segs.s[k].rows) ++k;
+    const LinSeg& sg = segs.s[k];
+    const int ro = o - sg.row0;
+    sg.dW[(size_t)ro * I + i] += s;
     if (i == 0) {
-        if (db) db[o] += sb;
-        if (db2) db2[o] += sb;
+        if (sg.db) sg.db[ro] += sb;
+        if (sg.db2) sg.db2[ro] += sb;
     }
 }
 // dx[b][i] = sum_o dy[b*ldy + o] * W[o][i]   (optionally * silu'(z[b][i]))
-__global__ void lin_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ Wt, float* __restrict__ dx,
-                                 const float* __restrict__ z, int rows, int O, int I) {
+__global__ void __launch_bounds__(256) lin_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ Wt,
+                                                        float* __restrict__ dx, const float* __restrict__ z, int rows, int O, int I) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * I) return;
     const int b = idx / I, i = idx - b * I;
-    float s = 0.f;
-    for (int o = 0; o < O; ++o) s = fmaf(dy[(size_t)b * ldy + o], Wt[(size_t)o * I + i], s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float* dr = dy + (size_t)b * ldy;
+    int o = 0;
+    for (; o + 4 <= O; o += 4) {
+        const float d0 = dr[o], d1 = dr[o + 1], d2 = dr[o + 2], d3 = dr[o + 3];
+        const float w0 = Wt[(size_t)o * I + i], w1 = Wt[(size_t)(o + 1) * I + i], w2 = Wt[(size_t)(o + 2) * I + i],
+                    w3 = Wt[(size_t)(o + 3) * I + i];
+        s0 = fmaf(d0, w0, s0); s1 = fmaf(d1, w1, s1); s2 = fmaf(d2, w2, s2); s3 = fmaf(d3, w3, s3);
+    }
+    for (; o < O; ++o) s0 = fmaf(dr[o], Wt[(size_t)o * I + i], s0);
+    float s = (s0 + s1) + (s2 + s3);
     if (z) {
         const float zz = z[idx];
         const float sg = 1.0f / (1.0f + __expf(-zz));
