@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=512)
+    ap.add_argument("--pairs-per-step", type=int, default=2048)
     ap.add_argument("--train-batch", type=int, default=256, help="per-GPU batch of the training-step measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()

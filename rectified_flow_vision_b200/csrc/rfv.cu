@@ -410,6 +410,12 @@ struct rfv_engine {
             int bregion;
             if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
             else { g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8); bregion = g.b_stages * bbytes; }
+            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) {  // wide images: the halo boxes need the room
+                g.resident_b = 0;
+                g.b_stages = 8;
+                bregion = g.b_stages * bbytes;
+            }
+            while (!g.resident_b && g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
             g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
             if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
             bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 512;

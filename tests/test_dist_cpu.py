@@ -58,3 +58,73 @@ def test_sharded_map_gloo_world2(tmp_path):
 def test_single_process_passthrough():
     rows = rdist.seeded_noise(3, 3, 4, 1)
     assert torch.equal(rdist.sharded_map(_fake_integrate, rows), _fake_integrate(rows))
+
+
+# ---- data-parallel training step: host-side sequence zero_grad -> accumulate -> all-reduce(SUM) -> step(1/world) ----
+class _StubEngine:
+    """Stands in for the native handle on a CPU box: gradient = mean of the shard, 'optimizer' = SGD on one weight."""
+
+    def __init__(self):
+        self.g = torch.zeros(3)
+        self.w = torch.zeros(3)
+        self.calls = []
+
+    def zero_grad(self):
+        self.g.zero_()
+        self.calls.append("zero")
+
+    def train_accumulate(self, x0, x1, t, dropout_p=0.0, seed=0):
+        self.g += (x1 - x0).mean(dim=0)
+        self.calls.append(("acc", dropout_p, seed))
+        return ((x1 - x0) ** 2).mean()
+
+    def grad_buffer(self):
+        return self.g
+
+    def optimizer_step(self, lr, step, b1, b2, eps, wd, max_norm, grad_scale=1.0):
+        self.calls.append(("step", step, grad_scale))
+        self.w -= lr * self.g * grad_scale
+        return (self.g * grad_scale).norm()
+
+
+class _StubNet:
+    dropout_p = 0.1
+
+    def __init__(self):
+        self.eng = _StubEngine()
+
+    def train_engine(self, size, device, micro_batch=None):
+        return self.eng
+
+
+class _StubModel:
+    device = "cpu"
+    training = True
+
+    def __init__(self):
+        self.velocity_net = _StubNet()
+
+
+def _train_worker(rank, world, port, out_dir):
+    from rectified_flow_vision_b200.training import NativeTrainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = _StubModel()
+    tr = NativeTrainer(m, lr=0.5)
+    data = torch.arange(12, dtype=torch.float32).view(4, 3)       # the global batch: 4 rows
+    lo, hi = rdist.shard_bounds(4, rank, world)
+    x1 = data[lo:hi]
+    tr.step(torch.zeros_like(x1), x1, torch.zeros(hi - lo))
+    torch.save({"w": m.velocity_net.eng.w, "calls": m.velocity_net.eng.calls}, os.path.join(out_dir, f"t{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_trainer_gloo_world2(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
+    want = -0.5 * torch.arange(12, dtype=torch.float32).view(4, 3).mean(dim=0)   # one SGD step on the GLOBAL mean gradient
+    assert torch.allclose(r0["w"], want) and torch.allclose(r1["w"], want)       # identical replicas after the step
+    assert r0["calls"][0] == "zero" and r0["calls"][1] == ("acc", 0.1, 1) and r0["calls"][2] == ("step", 1, 0.5)

@@ -138,3 +138,28 @@ def test_train_rectified_flow_api_reduces_loss():
     losses = pkg.train_rectified_flow(m, x0, x1, epochs=4, batch_size=16, lr=1e-3)
     assert len(losses) == 4 and all(np.isfinite(losses))
     assert losses[-1] < 0.6 * losses[0], losses
+
+
+def test_config5_128x128_forward_and_training_step():
+    """BASELINE.json configs[4]: the config.yaml UNet at 128x128 (attention over 1024 tokens, 129-pixel halo pitch).
+    No reference golden exists at this size; the CPU fp32 port (itself pinned to the reference at 32/64) is the checker."""
+    import rectified_flow_vision_b200 as pkg
+    from oracle import torch_port, train_oracle as T
+    torch.manual_seed(0)
+    m = pkg.BaseFlowModel(image_size=128, device="cuda:0")
+    m.eval()
+    g = torch.Generator().manual_seed(42)
+    x, x1, t = torch.randn(2, 3, 128, 128, generator=g), torch.randn(2, 3, 128, 128, generator=g), torch.rand(2, generator=g)
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    v = m(x.cuda(), t.cuda()).cpu().numpy()
+    ref = torch_port.unet_forward(P, x, t).numpy()
+    assert util.rel_l2(v, ref) <= 3e-2 and util.max_rel(v, ref) <= 5e-2
+    loss_ref, grads = T.loss_and_grads(P, x, x1, t)
+    eng = m.velocity_net.train_engine(128, "cuda:0", micro_batch=2)
+    eng.zero_grad()
+    loss = float(eng.train_accumulate(x.cuda(), x1.cuda(), t.cuda(), 0.0, 1).item())
+    assert abs(loss - loss_ref) <= TOL_LOSS * loss_ref
+    for k in ("velocity_net.mid_attn.qkv.weight", "velocity_net.enc_blocks.0.conv1.weight", "velocity_net.dec_blocks.5.conv2.weight",
+              "velocity_net.upsamples.1.1.weight", "velocity_net.downsamples.0.weight", "velocity_net.input_conv.weight"):
+        got = eng.get_grad(k, grads[k].numel()).cpu().numpy().reshape(grads[k].shape)
+        assert util.rel_l2(got, grads[k].numpy()) <= TOL_GRAD_L2, k
