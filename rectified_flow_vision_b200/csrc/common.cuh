@@ -133,6 +133,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* map, uint64_
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): `bytes` multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // Multicast variant: the box lands at the same shared-memory offset in every CTA of `mask` and completes bytes on the
 // mbarrier at the same offset in each of them (weights shared by the CTAs of a cluster are fetched from L2 once).
 __device__ __forceinline__ void tma_load_2d_mc(void* smem, const void* map, uint64_t* bar, int c0, int c1, uint16_t mask) {

@@ -16,7 +16,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 __device__ __forceinline__ void dropout_mask8(uint32_t seed, uint32_t elem0, uint32_t thresh, float scale, float* m) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t h = mix32(seed ^ (((elem0 >> 1) + k) * 0x9E3779B1u));
+        uint32_t h = (seed ^ ((elem0 >> 1) + k)) * 0x9E3779B1u;   // two multiply / xor-shift rounds: enough to decorrelate
+        h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13;                 // neighbouring counters for a Bernoulli mask
         m[2 * k] = (h & 0xFFFFu) >= thresh ? scale : 0.f;
         m[2 * k + 1] = (h >> 16) >= thresh ? scale : 0.f;
     }
@@ -65,6 +66,16 @@ __device__ __forceinline__ void gn_group_stats(const GnBwdArgs& a, int n, int g,
     *rstd = rsqrtf(fmaxf(ss / cnt - m * m, 0.f) + a.eps);
 }
 
+// sigmoid through the hardware tanh (one MUFU op instead of ex2 + rcp): |error| ~ 2.5e-4, far below bf16 resolution
+__device__ __forceinline__ float sigmoid_fast(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
+}
+
+// Arithmetic is arranged so that the per-element work is a handful of FMAs (these kernels are issue-bound, not HBM-bound,
+// when written naively):  z = x*sc + sh;  silu'(z) = sg + z*(sg - sg^2);  pass 1 accumulates sum(dz) and sum(dz*x) and
+// converts to sum(dz*xhat) at the end;  pass 2 is dx = dz*k1[c] + x*k2 + k3 with per-group constants k2, k3.
 template <bool APPLY>
 __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     extern __shared__ float sm[];   // reduce: [2*C] partial sums
@@ -96,9 +107,12 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
     const int grp = (cv * 8) / cpg;
     const float mean = gmean[grp], rstd = grstd[grp];
-    float gam[8], bet[8];
+    float sc[8], sh[8];   // z = x*sc + sh with sc = rstd*gamma (also the dz coefficient of dx)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gam[j] = a.gamma[cv * 8 + j]; bet[j] = a.beta[cv * 8 + j]; }
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = rstd * a.gamma[cv * 8 + j];
+        sh[j] = a.beta[cv * 8 + j] - mean * sc[j];
+    }
     const bool from_a = cv * 8 < a.Ca;
     const bf16* src = from_a ? a.xa + cv * 8 : a.xb + (cv * 8 - a.Ca);
     const int cs_ = from_a ? a.Ca : a.Cb;
@@ -111,6 +125,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
     const float s1 = APPLY ? gS1[grp] : 0.f, s2 = APPLY ? gS2[grp] : 0.f;
+    const float k2 = -rstd * rstd * s2, k3 = -rstd * s1 - mean * k2;   // dx = dz*sc + x*k2 + k3
     const bool has_cat = APPLY && a.add_cat != nullptr, has_a = APPLY && a.add_a != nullptr && from_a;
     constexpr int U = 2;
     for (int pp = pl; pp < np; pp += U * pstride) {
@@ -137,15 +152,14 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
             float r[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float xh = (x[j] - mean) * rstd;
                 float dz = a.drop_thresh ? d[j] * mk[j] : d[j];
                 if (a.silu) {
-                    const float z = fmaf(gam[j], xh, bet[j]);
-                    const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
-                    dz *= sg * (1.0f + z * (1.0f - sg));
+                    const float z = fmaf(x[j], sc[j], sh[j]);
+                    const float sg = sigmoid_fast(z);
+                    dz *= fmaf(z, fmaf(-sg, sg, sg), sg);
                 }
-                if (APPLY) r[j] = rstd * (gam[j] * dz - s1 - xh * s2);
-                else { accA[j] += dz; accB[j] += dz * xh; }
+                if (APPLY) r[j] = fmaf(dz, sc[j], fmaf(x[j], k2, k3));
+                else { accA[j] += dz; accB[j] = fmaf(dz, x[j], accB[j]); }
             }
             if (APPLY) {
                 float f[8];
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             atomicAdd(&sm[(cv * 8 + j) * 2], accA[j]);
-            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], accB[j]);
+            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], rstd * (accB[j] - mean * accA[j]));   // sum dz*xhat
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.cs + (size_t)n * C * 2 + i, sm[i]);

@@ -31,7 +31,9 @@ constexpr int WG_THREADS = 256;
 
 struct WgradGeom {
     int pitch, R, tiles_per_img, ksteps;
-    int cchA, cchB, nvar;          // 64-channel chunks of A / of dY; A variants (1, or 4 parity views)
+    int cchA, cchB, nvar;          // 64-channel chunks of A; N-chunks (64*ncob channels) of dY; variants (tap groups / parity views)
+    int ncob;                      // 64-channel dY boxes per N-chunk: N = 64 (1) or 128 (2) per MMA
+    int b_sub_bytes;               // bytes from one dY box to the next inside a stage
     int a_stage_bytes, b_stage_bytes, stages;
     int a_box_bytes, b_box_bytes;
     int ldw;                       // floats per gradient row
@@ -100,16 +102,17 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (elect_one()) {
                 uint8_t* sa = smem + (size_t)st * stage_bytes;
                 uint8_t* sb = sa + g.a_stage_bytes;
-                mbar_arrive_expect_tx(&full[st], g.a_box_bytes + g.b_box_bytes);
+                mbar_arrive_expect_tx(&full[st], g.a_box_bytes + g.ncob * g.b_box_bytes);
                 const CUtensorMap* ma = var == 0 ? &mapA0 : (var == 1 ? &mapA1 : (var == 2 ? &mapA2 : &mapA3));
                 tma_load_4d(sa + 1024, ma, &full[st], a * 64, -1, r0 - 1, n);
-                tma_load_4d(sb, &mapY, &full[st], b * 64, -1, r0, n);
+                for (int j = 0; j < g.ncob; ++j) tma_load_4d(sb + j * g.b_sub_bytes, &mapY, &full[st], (b * g.ncob + j) * 64, -1, r0, n);
             }
             __syncwarp();
             if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);  // both operands MN-major
+        const int N = 64 * g.ncob;
+        const uint32_t idesc = umma_idesc_bf16(128, N) | (1u << 15) | (1u << 16);  // both operands MN-major
         uint32_t st = 0, ph = 0, accph = 0;
         int cur_pair = -1;
         bool first = true;
@@ -132,10 +135,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const uint32_t sb = sa - 1024 + g.a_stage_bytes;
                 const int nu = g.nunits[var];
                 for (int ks = 0; ks < g.ksteps; ++ks) {
-                    const uint64_t bdesc = umma_desc_mn_sw128(sb + ks * 2048, 1024);
+                    const uint64_t bdesc = umma_desc_mn_sw128(sb + ks * 2048, (uint32_t)g.b_sub_bytes);  // LBO: next 64 output channels
                     for (int u = 0; u < nu; ++u) {
                         const uint64_t adesc = umma_desc_mn_sw128(sa + (uint32_t)((g.u_shift[var][u] + ks * 16) * 128), (uint32_t)g.u_lbo[var][u]);
-                        umma_bf16(tmem_base + u * 64, adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
+                        umma_bf16(tmem_base + u * N, adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
                     }
                 }
                 umma_commit(&empty[st]);
@@ -159,16 +162,16 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             mbar_wait(acc_full, fph);
             fph ^= 1;
             tc_fence_after();
-            const int nu = g.nunits[var];
+            const int nu = g.nunits[var], N = 64 * g.ncob;
             for (int u = 0; u < nu; ++u) {
                 const int koff = row < 64 ? g.u_koff0[var][u] : g.u_koff1[var][u];  // warp-uniform (q < 2 / q >= 2)
 #pragma unroll 1
-                for (int ch = 0; ch < 2; ++ch) {
+                for (int ch = 0; ch < N / 32; ++ch) {
                     uint32_t acc[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + u * 64 + ch * 32, acc);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + u * N + ch * 32, acc);
                     tmem_ld_wait();
                     if (koff >= 0) {
-                        float* dst = dW + (size_t)(b * 64 + ch * 32) * g.ldw + koff + a * 64 + (row & 63);
+                        float* dst = dW + (size_t)(b * N + ch * 32) * g.ldw + koff + a * 64 + (row & 63);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * g.ldw, __uint_as_float(acc[j]));
                     }
@@ -187,41 +190,65 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 // W, H: dY (conv output) grid.  kind 0: 3x3 stride 1 (taps = 9 shifts of one box); kind 1: 1x1; kind 2: 3x3 stride 2
 // (A variants = the four parity views (ph,pw) of the input, dims W x H each).  Cin, Cout multiples of 64.
 // koff_base: column of this conv's first weight inside the gradient row (shortcut segments live after the 3x3 part).
-inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int kind, int ldw, int koff_base) {
+inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int kind, int ldw, int koff_base, int allow_n128 = 1) {
     *g = WgradGeom{};
     g->pitch = W + 1;
+    // N = 128 per MMA runs the tensor pipe at 79 % instead of 39 % (measured 81-cycle floor per instruction); it needs the
+    // nine taps of a 3x3 conv split into two variants (5 + 4 taps) because 9 x 64 x 128 fp32 accumulators exceed TMEM
+    g->ncob = (allow_n128 && Cout % 128 == 0) ? 2 : 1;
+    const int avail = 227 * 1024 - 1024 - 256;
     int R = 1;
     while (R * 2 <= H && R * 2 * g->pitch <= 272) R *= 2;
-    g->R = R;
-    g->tiles_per_img = (H + R - 1) / R;
-    g->ksteps = (R * g->pitch + 15) / 16;
-    g->cchA = Cin / 64; g->cchB = Cout / 64;
-    g->nvar = kind == 2 ? 4 : 1;
-    g->a_box_bytes = (R + 2) * g->pitch * 128;
-    g->b_box_bytes = R * g->pitch * 128;
-    g->a_stage_bytes = 1024 + ((g->a_box_bytes + 17 * 128 + 1023) & ~1023);
-    g->b_stage_bytes = (g->ksteps * 2048 + 1023) & ~1023;
-    const int avail = 227 * 1024 - 1024 - 256;
-    g->stages = avail / (g->a_stage_bytes + g->b_stage_bytes);
+    for (;; R /= 2) {
+        g->R = R;
+        g->ksteps = (R * g->pitch + 15) / 16;
+        g->a_box_bytes = (R + 2) * g->pitch * 128;
+        g->b_box_bytes = R * g->pitch * 128;
+        g->a_stage_bytes = 1024 + ((g->a_box_bytes + 17 * 128 + 1023) & ~1023);
+        g->b_sub_bytes = (g->ksteps * 2048 + 1023) & ~1023;
+        g->b_stage_bytes = g->ncob * g->b_sub_bytes;
+        g->stages = avail / (g->a_stage_bytes + g->b_stage_bytes);
+        if (g->stages >= 2 || R == 1) break;
+    }
     if (g->stages > 4) g->stages = 4;
     if (g->stages < 2) return false;
+    g->tiles_per_img = (H + g->R - 1) / g->R;
+    g->cchA = Cin / 64; g->cchB = Cout / (64 * g->ncob);
+    const int max_units = 512 / (64 * g->ncob) > WG_MAX_UNITS ? WG_MAX_UNITS : 512 / (64 * g->ncob);
     g->ldw = ldw;
-    for (int var = 0; var < g->nvar; ++var) {
-        int shift[9], koff[9], na = 0;
-        if (kind == 0) {
-            for (int tap = 0; tap < 9; ++tap) { shift[na] = (tap / 3) * g->pitch + (tap % 3 - 1); koff[na] = koff_base + tap * Cin; ++na; }
-        } else if (kind == 1) {
-            shift[0] = g->pitch; koff[0] = koff_base; na = 1;
-        } else {
-            // parity view (ph,pw): in[2i+ph, 2j+pw]; tap ky reads row 2i+ky-1: ky=1 -> ph 0 shift 0; ky=0 -> ph 1 shift -1; ky=2 -> ph 1 shift 0
+    // atoms (tap shifts) per variant
+    int vshift[4][9], vkoff[4][9], vn[4] = {0, 0, 0, 0};
+    if (kind == 0) {
+        const int split = g->ncob == 2 ? 5 : 9;   // variant 0: taps [0, split), variant 1: the rest
+        g->nvar = g->ncob == 2 ? 2 : 1;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int v = tap < split ? 0 : 1;
+            vshift[v][vn[v]] = (tap / 3) * g->pitch + (tap % 3 - 1);
+            vkoff[v][vn[v]] = koff_base + tap * Cin;
+            ++vn[v];
+        }
+    } else if (kind == 1) {
+        g->nvar = 1;
+        vshift[0][0] = g->pitch; vkoff[0][0] = koff_base; vn[0] = 1;
+    } else {
+        // parity view (ph,pw): in[2i+ph, 2j+pw]; tap ky reads row 2i+ky-1: ky=1 -> ph 0 shift 0; ky=0 -> ph 1 shift -1; ky=2 -> ph 1 shift 0
+        g->nvar = 4;
+        for (int var = 0; var < 4; ++var) {
             const int ph = var >> 1, pw = var & 1;
             for (int ky = 0; ky < 3; ++ky)
                 for (int kx = 0; kx < 3; ++kx) {
                     if (((ky + 1) & 1) != ph || ((kx + 1) & 1) != pw) continue;
                     const int dy = ky == 0 ? -1 : 0, dx = kx == 0 ? -1 : 0;
-                    shift[na] = (1 + dy) * g->pitch + dx; koff[na] = koff_base + (ky * 3 + kx) * Cin; ++na;
+                    vshift[var][vn[var]] = (1 + dy) * g->pitch + dx;
+                    vkoff[var][vn[var]] = koff_base + (ky * 3 + kx) * Cin;
+                    ++vn[var];
                 }
         }
+    }
+    for (int var = 0; var < g->nvar; ++var) {
+        const int na = vn[var];
+        const int* shift = vshift[var];
+        const int* koff = vkoff[var];
         int nu = 0;
         for (int i = 0; i + 1 < na; i += 2) {
             g->u_shift[var][nu] = shift[i]; g->u_lbo[var][nu] = (shift[i + 1] - shift[i]) * 128;
@@ -232,6 +259,7 @@ inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int k
             else { g->u_shift[var][nu] = shift[na - 2]; g->u_lbo[var][nu] = (shift[na - 1] - shift[na - 2]) * 128; g->u_koff0[var][nu] = -1; g->u_koff1[var][nu] = koff[na - 1]; }
             ++nu;
         }
+        if (nu > max_units) return false;
         g->nunits[var] = nu;
     }
     return true;

@@ -28,7 +28,7 @@ static void make_map4(CUtensorMap* m, const bf16* base, int C, int Wd, int Hd, i
 static float bf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // kind 0: 3x3 s1, 1: 1x1, 2: 3x3 s2.  Wo,Ho = output grid.
-static int run(int kind, int Wo, int Ho, int Cin, int Cout, int B) {
+static int run(int kind, int Wo, int Ho, int Cin, int Cout, int B, int n128 = 1) {
     const int Wi = kind == 2 ? 2 * Wo : Wo, Hi = kind == 2 ? 2 * Ho : Ho;
     const int taps = kind == 1 ? 1 : 9;
     const int K = taps * Cin;
@@ -45,7 +45,7 @@ static int run(int kind, int Wo, int Ho, int Cin, int Cout, int B) {
     cudaMemcpy(ddy, dyb.data(), dyb.size() * 2, cudaMemcpyHostToDevice);
     cudaMemset(dW, 0, (size_t)Cout * K * 4);
     WgradGeom g;
-    if (!make_wgrad_geom(&g, Wo, Ho, Cin, Cout, kind, K, 0)) { printf("geom failed\n"); return 1; }
+    if (!make_wgrad_geom(&g, Wo, Ho, Cin, Cout, kind, K, 0, n128)) { printf("geom failed\n"); return 1; }
     g.num_tiles = B * g.tiles_per_img;
     CUtensorMap ma[4], my;
     if (kind != 2) {
@@ -96,7 +96,7 @@ static int run(int kind, int Wo, int Ho, int Cin, int Cout, int B) {
     for (size_t i = 0; i < ref.size(); ++i) { const double d = out[i] - ref[i]; num += d * d; den += ref[i] * ref[i]; maxd = std::max(maxd, std::fabs(d)); }
     const double rel = std::sqrt(num / std::max(den, 1e-30));
     const double fl = 2.0 * B * Ho * Wo * (double)Cout * K;
-    printf("kind=%d %dx%d Cin=%d Cout=%d B=%d R=%d ksteps=%d stages=%d grid=%d: rel-L2 %.3e max|d| %.3e  %.3f ms %.1f TFLOP/s  %s\n", kind, Wo, Ho,
+    printf("kind=%d N=%d %dx%d Cin=%d Cout=%d B=%d R=%d ksteps=%d stages=%d grid=%d: rel-L2 %.3e max|d| %.3e  %.3f ms %.1f TFLOP/s  %s\n", kind, 64 * g.ncob, Wo, Ho,
            Cin, Cout, B, g.R, g.ksteps, g.stages, grid, rel, maxd, ms, fl / ms / 1e9, rel < 1e-3 ? "OK" : "MISMATCH");
     if (rel >= 1e-3) {
         // diagnose: per-tap relative error for co=0..1
@@ -126,7 +126,15 @@ int main() {
     bad += run(1, 16, 16, 256, 768, 4);
     bad += run(0, 8, 8, 64, 64, 5);
     bad += run(0, 64, 64, 64, 64, 64);    // timing-sized
-    bad += run(0, 16, 16, 256, 256, 64);
+    bad += run(0, 16, 16, 256, 256, 64, 0);
+    bad += run(0, 16, 16, 256, 256, 64, 1);
+    bad += run(0, 32, 32, 128, 128, 64, 0);
+    bad += run(0, 32, 32, 128, 128, 64, 1);
+    bad += run(0, 64, 64, 128, 128, 32, 0);
+    bad += run(0, 64, 64, 128, 128, 32, 1);
+    bad += run(2, 16, 16, 128, 128, 8, 1);
+    bad += run(1, 16, 16, 256, 768, 64, 0);
+    bad += run(1, 16, 16, 256, 768, 64, 1);
     printf(bad ? "FAILED %d\n" : "ALL OK\n", bad);
     return bad;
 }
