@@ -95,3 +95,23 @@ def test_c_abi_exports_every_declared_symbol():
     # argument checking works without a GPU (no compute call is made)
     assert lib.rfv_create(None, None) != 0
     assert b"null" in lib.rfv_last_error()
+
+
+def test_benchmark_csv_schema_matches_reference(tmp_path):
+    """experiments/benchmark.py:252-262 writes num_steps,base_time_ms,rect_time_ms,base_img_per_sec,rect_img_per_sec,speedup."""
+    from rectified_flow_vision_b200 import benchmark as B
+
+    class Stub:
+        def eval(self):
+            return self
+
+        def sample(self, noise=None, num_steps=1):
+            return noise
+
+    br = B.benchmark_speed(Stub(), 8, [1, 2], 8, "cpu", num_runs=2, batch_size=4)
+    assert [set(r) for r in br] == [{'num_steps', 'total_time', 'time_per_image', 'images_per_second', 'time_std', 'num_samples'}] * 2
+    out = tmp_path / "results" / "benchmark_results.csv"
+    B.write_results_csv(str(out), br, br)
+    lines = out.read_text().strip().splitlines()
+    assert lines[0] == "num_steps,base_time_ms,rect_time_ms,base_img_per_sec,rect_img_per_sec,speedup"
+    assert len(lines) == 3 and lines[1].startswith("1,") and lines[1].endswith(",1.0")

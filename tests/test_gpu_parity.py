@@ -170,3 +170,11 @@ def test_errors_are_loud():
     with pytest.raises(E.RfvError):
         E.Engine(dict(in_channels=3, model_channels=48, out_channels=3, channel_mult=[1, 2], num_res_blocks=1), 32,
                  torch.device("cuda:0"))
+
+
+def test_benchmark_driver_runs_on_gpu(tmp_path):
+    from rectified_flow_vision_b200 import benchmark as B
+    m = util.seeded_model("small32", device="cuda:0")
+    res = B.benchmark_speed(m, 8, [1, 2], 32, "cuda", num_runs=2, batch_size=4)
+    assert [r["num_steps"] for r in res] == [1, 2] and all(r["images_per_second"] > 0 for r in res)
+    B.write_results_csv(str(tmp_path / "b.csv"), res, res)
