@@ -60,6 +60,7 @@ typedef struct {
                                   B200: WRONG results -- the 128B swizzle is applied on absolute smem address bits, so
                                   shifted (128-byte aligned) start addresses need base offset 0.  Kept as an experiment. */
 
+#define RFV_FLAG_NO_PAIR   64  /* 64-output-channel 3x3 convs: one tap per MMA (N = 64) instead of two (N = 128); A/B testing */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

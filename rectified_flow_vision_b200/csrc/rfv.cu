@@ -23,6 +23,7 @@
 #include "conv_mma.cuh"
 #include "conv_params.h"
 #include "conv_halo.cuh"
+#include "conv_halo_pair.cuh"
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
@@ -135,7 +136,7 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true;
+    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true;
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
@@ -389,7 +390,54 @@ struct rfv_engine {
         if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
         const bool halo_ok = umma_ok && use_halo && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
                              (out->W == 32 || out->W == 64 || out->W == 128);
-        if (halo_ok) {
+        if (halo_ok && use_pair && L->Cout % 128 != 0 && (L->C0 >= 128 || L->Cout > 64)) {
+            // 64-output-channel tiles: two taps per MMA (conv_halo_pair.cuh)
+            struct PBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; size_t smem; };
+            auto bd = std::make_shared<PBundle>();
+            HaloGeom& g = bd->g;
+            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
+            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
+            g.tiles_per_img = (g.H * g.pitch + 126) / 127;   // tiles advance by 127 positions
+            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+            g.n_tiles = L->Cout / 64;
+            g.a_box_bytes = g.rows * g.pitch * 128;
+            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
+            g.base_offset_mode = 0;
+            const int nblk = 9 * g.cch0 + g.cch1a + g.cch1b;
+            const int avail = 227 * 1024 - 2048 - 512 - HP_XCH_BYTES;
+            g.resident_b = (g.n_tiles == 1 && (size_t)nblk * HP_BLK <= 96 * 1024) ? 1 : 0;
+            int bregion = nblk * HP_BLK;
+            g.b_stages = 1;
+            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) g.resident_b = 0;
+            if (!g.resident_b) {
+                g.b_stages = 3;
+                bregion = g.b_stages * HP_TRI;
+                while (g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * HP_TRI;
+            }
+            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
+            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: paired halo tile does not fit shared memory", L->name.c_str());
+            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 256 + HP_XCH_BYTES;
+            auto amap = [&](CUtensorMap* m, const ActP& t) {
+                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
+            };
+            RFV_TRY(amap(&bd->a0, in0));
+            bd->a1 = bd->a0; bd->a2 = bd->a0;
+            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
+            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, 64));
+            const int sms = num_sms, sumC_ = sumC;
+            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
+                ConvParams q = p;
+                q.B = rc.B;
+                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                HaloGeom g = bd->g;
+                g.m_tiles = rc.B * g.tiles_per_img;
+                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
+                conv_halo_pair_kernel<<<grid, HP_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                return cudaGetLastError();
+            });
+        } else if (halo_ok) {
             struct HBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; int BN; size_t smem; };
             auto bd = std::make_shared<HBundle>();
             HaloGeom& g = bd->g;
@@ -846,6 +894,7 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
     std::vector<int> chans(nlev);
@@ -1397,6 +1446,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
+    e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
     if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {
