@@ -780,7 +780,8 @@ struct rfv_engine {
     // dW slot of parameter `pi` (+)= wgrad(dy, a).  kind as make_wgrad_geom; a: the conv's input activations (for
     // kind 2 the full-resolution tensor); dy: [cap, Ho, Wo, Cout].  The slot row holds ldw floats, this conv's columns
     // start at koff_base (second source of a shortcut over a virtual concat).
-    int bwd_wgrad(const std::string& label, int kind, const ActP& a, const bf16* dy, int Cout, int Wo, int Ho, int pi, int ldw, int koff_base) {
+    int bwd_wgrad(const std::string& label, int kind, const ActP& a, const bf16* dy, int Cout, int Wo, int Ho, int pi, int ldw, int koff_base,
+                  float* dst_override = nullptr) {
         struct Bundle { CUtensorMap ma[4], my; WgradGeom g; size_t smem; };
         auto bd = std::make_shared<Bundle>();
         if (a->C % 64 != 0 || Cout % 64 != 0) return fail(RFV_ERR_INVALID, "wgrad %s: channel counts must be multiples of 64", label.c_str());
@@ -800,12 +801,13 @@ struct rfv_engine {
         const int taps = kind == 1 ? 1 : 9;
         const double fl = 2.0 * taps * a->C * Cout * Ho * Wo;
         const int sms = num_sms;
-        push("wgrad_umma", "bwd:wgrad:" + label, fl, [this, bd, pi, sms](const RunCtx& rc, cudaStream_t s) {
+        push("wgrad_umma", "bwd:wgrad:" + label, fl, [this, bd, pi, sms, dst_override](const RunCtx& rc, cudaStream_t s) {
             WgradGeom g = bd->g;
             g.num_tiles = rc.B * g.tiles_per_img;
             const long long total = (long long)g.nvar * g.cchA * g.cchB * g.num_tiles;
             const int grid = (int)std::min<long long>(total, sms);
-            wgrad_umma_kernel<<<grid, WG_THREADS, bd->smem, s>>>(bd->ma[0], bd->ma[1], bd->ma[2], bd->ma[3], bd->my, gslot(pi), g);
+            wgrad_umma_kernel<<<grid, WG_THREADS, bd->smem, s>>>(bd->ma[0], bd->ma[1], bd->ma[2], bd->ma[3], bd->my,
+                                                                 dst_override ? dst_override : gslot(pi), g);
             return cudaGetLastError();
         });
         return 0;
@@ -916,7 +918,6 @@ int rfv_engine::build() {
     }
     RFV_TRY(dalloc(&stats_arena, stats_floats));
     if (train) {
-        if (mc != 64) return fail(RFV_ERR_INVALID, "training supports model_channels == 64 (got %d)", mc);
         int cmax = 0;
         size_t need = 0;  // largest per-image backward temporary (elements)
         for (int lv = 0; lv < nlev; ++lv) {
@@ -1031,14 +1032,24 @@ int rfv_engine::build() {
         named_acts["input_conv"] = h;
         if (train) {
             RFV_TRY(ensure_grad(h));
-            if (mc != 64) return fail(RFV_ERR_INVALID, "training: the thin-conv weight-gradient kernel is sized for model_channels == 64 (got %d)", mc);
-            const size_t sw_smem = ((size_t)256 * (mc + 2) * 2 + 15 & ~(size_t)15) + (size_t)4 * 10 * 34 * sizeof(float);
-            CU_CHECK(cudaFuncSetAttribute(small_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem));
+            float* wscr = nullptr;   // padded weight gradient [mc][9][64]
+            RFV_TRY(dalloc(&wscr, (size_t)mc * 9 * 64));
             begin_bwd();
             const bf16* dh = h->grad;
-            const int sms = num_sms;
-            push("small_wgrad", "bwd:wgrad:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-                small_wgrad_kernel<<<2 * sms, 256, sw_smem, s>>>(dh, rc.x, rc.x1, rc.t, gslot(iw), rc.B, S, S, mc, Cin, +1, 0);
+            ActP xpad;
+            RFV_TRY(scratch_act(&xpad, 0, 64, S, S));
+            {
+                bf16* xp = xpad->p;
+                push("elementwise_bwd", "bwd:pad:input_conv", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                    cudaError_t e = cudaMemsetAsync(wscr, 0, (size_t)mc * 9 * 64 * sizeof(float), s);
+                    if (e != cudaSuccess) return e;
+                    pad_to_nhwc64_kernel<<<2048, 256, 0, s>>>(rc.x, rc.x1, rc.t, xp, rc.B, Cin, S * S);
+                    return cudaGetLastError();
+                });
+            }
+            RFV_TRY(bwd_wgrad("input_conv", 0, xpad, dh, mc, S, S, iw, 9 * 64, 0, wscr));
+            push("elementwise_bwd", "bwd:extract:input_conv", 0.0, [=](const RunCtx&, cudaStream_t s) {
+                extract_wgrad_kernel<<<(mc * Cin * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), mc, Cin, 64);
                 return cudaGetLastError();
             });
             bwd_colsum("input_conv.bias", dh, mc, S * S, nullptr, 0, ib, -1);
@@ -1280,13 +1291,26 @@ int rfv_engine::build() {
             begin_bwd();
             ActP T0;
             RFV_TRY(scratch_act(&T0, 0, C, S, S));
-            const size_t sw_smem = (((size_t)256 * (C + 2) * 2 + 15) & ~(size_t)15) + (size_t)4 * 10 * 34 * sizeof(float);
             const size_t ic_smem = ((size_t)Co * 9 * C + C + (C / 8) * 2) * sizeof(float);
             bf16* t0 = T0->p;
             const int ss = slab_shift;
-            push("small_wgrad", "bwd:wgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-                small_wgrad_kernel<<<2 * sms, 256, sw_smem, s>>>(ap, dv_buf, nullptr, nullptr, gslot(iw), rc.B, S, S, C, Co, -1, 1);
-                nchw_channel_sum_kernel<<<dim3(64, Co), 256, 0, s>>>(dv_buf, gslot(ib), rc.B, Co, S * S);
+            float* wscr = nullptr;   // padded weight gradient [64][9][C]
+            RFV_TRY(dalloc(&wscr, (size_t)64 * 9 * C));
+            ActP dvpad;
+            RFV_TRY(scratch_act(&dvpad, 1, 64, S, S));
+            {
+                bf16* dp = dvpad->p;
+                push("elementwise_bwd", "bwd:pad:output_conv.2", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                    cudaError_t e = cudaMemsetAsync(wscr, 0, (size_t)64 * 9 * C * sizeof(float), s);
+                    if (e != cudaSuccess) return e;
+                    pad_to_nhwc64_kernel<<<2048, 256, 0, s>>>(dv_buf, nullptr, nullptr, dp, rc.B, Co, S * S);
+                    nchw_channel_sum_kernel<<<dim3(64, Co), 256, 0, s>>>(dv_buf, gslot(ib), rc.B, Co, S * S);
+                    return cudaGetLastError();
+                });
+            }
+            RFV_TRY(bwd_wgrad("output_conv.2", 0, a, dvpad->p, 64, S, S, iw, 9 * C, 0, wscr));
+            push("elementwise_bwd", "bwd:extract:output_conv.2", 0.0, [=](const RunCtx&, cudaStream_t s) {
+                extract_wgrad_kernel<<<(Co * C * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), Co, C, C);
                 return cudaGetLastError();
             });
             push("input_conv", "bwd:dgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {

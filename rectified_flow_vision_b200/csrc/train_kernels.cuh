@@ -294,96 +294,41 @@ __global__ void sumpool2x2_kernel(const bf16* __restrict__ in, bf16* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Weight gradient of the two thin convolutions (input conv 3->64, output conv 64->3; models/unet.py:165,226):
-//   acc[c][s][tap] = sum_{n,pix} big[n,pix,c] * small[n,s,pix + sgn*off(tap)]
-// big: NHWC bf16 with Cb (<= 64) channels; small: NCHW fp32 with Cs (<= 4) channels, optionally the interpolation
-// (1-t) x0 + t x1 formed on the fly.  sgn=+1, out[(c*Cs+s)*9+tap]: input conv (big = dY, small = x_t);
-// sgn=-1, out[(s*Cb+c)*9+tap]: output conv (big = activations, small = dv).
-// Persistent blocks walk 8x32-pixel tiles, accumulate in registers and flush once with atomics.
+// The two thin convolutions (input conv 3->mc, output conv mc->3; models/unet.py:165,226) get their weight gradient from
+// the tcgen05 wgrad kernel too: the 3-channel NCHW fp32 tensor (x_t, or the loss gradient dv) is widened to a 64-channel
+// NHWC bf16 tensor (zero padding), the kernel writes a padded [O][9][Ipad] fp32 gradient into a scratch buffer and the real
+// rows / columns are added into the parameter's slot in reference layout.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) small_wgrad_kernel(const bf16* __restrict__ big, const float* __restrict__ sm0,
-                                                          const float* __restrict__ sm1, const float* __restrict__ tvec,
-                                                          float* __restrict__ out, int B, int H, int W, int Cb, int Cs, int sgn,
-                                                          int out_mode) {
-    // thread = (channel PAIR cp, combo group grp): one 32-bit shared load brings two channels of a pixel, each
-    // small-tensor value is reused for both; offsets of the thread's (s, tap) combos are precomputed.
-    constexpr int TH = 8, TW = 32, SW = TW + 2, MAXK = 8;
-    extern __shared__ __align__(16) uint8_t smraw[];
-    bf16* bt = reinterpret_cast<bf16*>(smraw);                               // [256][Cb+2]
-    const int bld = Cb + 2;
-    float* st = reinterpret_cast<float*>(smraw + ((256 * bld * 2 + 15) & ~15));  // [Cs][TH+2][TW+2]
-    const int tw = (W + TW - 1) / TW, th = (H + TH - 1) / TH, ntiles = tw * th * B;
-    const int tid = threadIdx.x;
-    const int npair = Cb / 2, ngrp = 256 / npair;              // Cb = 64: 32 pairs x 8 groups
-    const int cp = tid % npair, grp = tid / npair;
-    const int ncombo = Cs * 9;
-    const int per = (ncombo + ngrp - 1) / ngrp;                // <= MAXK (host checks)
-    int off[MAXK];
+// out[n, pix, 0:C] = (1-t) x0 + t x1 (or x0), out[n, pix, C:64] = 0
+__global__ void __launch_bounds__(256) pad_to_nhwc64_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                                            const float* __restrict__ tvec, bf16* __restrict__ out, int B, int C, int HW) {
+    const size_t total = (size_t)B * HW;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = idx / HW, p = idx - n * HW;
+        const float tb = x1 ? tvec[n] : 0.f;
+        float f[8];
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k) {
-        const int combo = grp * per + k;
-        if (k < per && combo < ncombo) {
-            const int s = combo / 9, tap = combo % 9;
-            off[k] = (s * (TH + 2) + 1 + sgn * (tap / 3 - 1)) * SW + 1 + sgn * (tap % 3 - 1);
-        } else off[k] = -1;
-    }
-    float acc0[MAXK], acc1[MAXK];
-#pragma unroll
-    for (int k = 0; k < MAXK; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int n = tile / (tw * th), r = tile - n * (tw * th);
-        const int h0 = (r / tw) * TH, w0 = (r % tw) * TW;
-        const float tb = sm1 ? tvec[n] : 0.f;
-        __syncthreads();
-        for (int i = tid; i < Cs * (TH + 2) * SW; i += 256) {
-            const int s = i / ((TH + 2) * SW), rr = i % ((TH + 2) * SW);
-            const int hh = h0 + rr / SW - 1, ww = w0 + rr % SW - 1;
+        for (int j = 0; j < 8; ++j) {
             float v = 0.f;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-                const size_t o = (((size_t)n * Cs + s) * H + hh) * W + ww;
-                v = sm0[o];
-                if (sm1) v = (1.0f - tb) * v + tb * sm1[o];
+            if (j < C) {
+                const size_t o = (n * C + j) * HW + p;
+                v = x0[o];
+                if (x1) v = (1.0f - tb) * v + tb * x1[o];
             }
-            st[i] = v;
+            f[j] = v;
         }
-        for (int i = tid; i < 256 * (Cb / 8); i += 256) {
-            const int p = i / (Cb / 8), cv = i % (Cb / 8);
-            const int hh = h0 + p / TW, ww = w0 + p % TW;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (hh < H && ww < W) q = *reinterpret_cast<const uint4*>(big + (((size_t)n * H + hh) * W + ww) * Cb + cv * 8);
-            uint32_t* d = reinterpret_cast<uint32_t*>(bt + p * bld + cv * 8);
-            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-        }
-        __syncthreads();
-        for (int ph = 0; ph < TH; ++ph) {
-#pragma unroll 4
-            for (int pw = 0; pw < TW; ++pw) {
-                const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bt + (ph * TW + pw) * bld + cp * 2));
-                const float* sp = st + ph * SW + pw;
+        uint4* o = reinterpret_cast<uint4*>(out + idx * 64);
+        o[0] = pack8(f);
 #pragma unroll
-                for (int k = 0; k < MAXK; ++k)
-                    if (off[k] >= 0) {
-                        const float x = sp[off[k]];
-                        acc0[k] = fmaf(v.x, x, acc0[k]);
-                        acc1[k] = fmaf(v.y, x, acc1[k]);
-                    }
-            }
-        }
+        for (int i = 1; i < 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
     }
-#pragma unroll
-    for (int k = 0; k < MAXK; ++k) {
-        const int combo = grp * per + k;
-        if (off[k] >= 0) {
-            const int s = combo / 9, tap = combo % 9, c = cp * 2;
-            if (out_mode == 0) {
-                atomicAdd(out + ((size_t)c * Cs + s) * 9 + tap, acc0[k]);
-                atomicAdd(out + ((size_t)(c + 1) * Cs + s) * 9 + tap, acc1[k]);
-            } else {
-                atomicAdd(out + ((size_t)s * Cb + c) * 9 + tap, acc0[k]);
-                atomicAdd(out + ((size_t)s * Cb + c + 1) * 9 + tap, acc1[k]);
-            }
-        }
-    }
+}
+// g[o][i][tap] += scratch[o*(9*Ipad) + tap*Ipad + i]   for o < O, i < I
+__global__ void extract_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ g, int O, int I, int Ipad) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= O * I * 9) return;
+    const int tap = idx % 9, i = (idx / 9) % I, o = idx / (9 * I);
+    g[idx] += scratch[(size_t)o * 9 * Ipad + tap * Ipad + i];
 }
 
 // Per-channel sums of an NCHW fp32 tensor with few channels (output-conv bias gradient).

@@ -188,3 +188,26 @@ def test_train_base_flow_and_iterative_reflow_end_to_end(tmp_path):
     assert (tmp_path / "reflow_k1_final.pt").exists() and (tmp_path / "reflow_k2_final.pt").exists()
     x = students[-1].sample(noise=torch.randn(2, 3, 32, 32, device="cuda:0"), num_steps=2)
     assert torch.isfinite(x).all()
+
+
+def test_training_with_model_channels_128():
+    """A wider network (model_channels = 128: 16-channel GroupNorm slabs, N = 128 weight-gradient tiles everywhere)."""
+    import rectified_flow_vision_b200 as pkg
+    from oracle import train_oracle as T
+    torch.manual_seed(3)
+    kw = dict(image_size=32, model_channels=128, channel_mult=[1, 2], num_res_blocks=1)
+    m = pkg.RectifiedFlowModel(device="cuda:0", **kw)
+    g = torch.Generator().manual_seed(9)
+    x0, x1, t = torch.randn(3, 3, 32, 32, generator=g), torch.randn(3, 3, 32, 32, generator=g), torch.rand(3, generator=g)
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    loss_ref, grads = T.loss_and_grads(P, x0, x1, t, model_channels=128, channel_mult=(1, 2), num_res_blocks=1)
+    eng = m.velocity_net.train_engine(32, "cuda:0", micro_batch=4)
+    eng.zero_grad()
+    loss = float(eng.train_accumulate(x0.cuda(), x1.cuda(), t.cuda(), 0.0, 1).item())
+    assert abs(loss - loss_ref) <= TOL_LOSS * loss_ref
+    gmax = max(float(v.norm()) for v in grads.values())
+    for k, gr in grads.items():
+        if float(gr.norm()) < 1e-3 * gmax:
+            continue
+        got = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape)
+        assert util.rel_l2(got, gr.numpy()) <= TOL_GRAD_L2, (k, util.rel_l2(got, gr.numpy()))
