@@ -61,6 +61,9 @@ typedef struct {
                                   shifted (128-byte aligned) start addresses need base offset 0.  Kept as an experiment. */
 
 #define RFV_FLAG_NO_PAIR   64  /* 64-output-channel 3x3 convs: one tap per MMA (N = 64) instead of two (N = 128); A/B testing */
+#define RFV_FLAG_DUAL      128 /* 256-output-channel convs: share each weight slice between two M tiles (conv_umma_dual_kernel).
+                                  Measured on B200 at micro-batch 256: 1.49 ms vs 1.43 ms for the 18 launches -- the lost
+                                  epilogue overlap costs more than the halved weight traffic gains; off by default. */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

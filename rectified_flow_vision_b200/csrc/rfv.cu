@@ -136,7 +136,7 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true;
+    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false;
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
@@ -492,7 +492,7 @@ struct rfv_engine {
                 return cudaGetLastError();
             });
         } else if (umma_ok) {
-            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; };
+            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; bool dual; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
             const int bw = std::min(gW, 128), bh = std::min(gH, 128 / bw), bn = 128 / (bw * bh);
@@ -524,6 +524,7 @@ struct rfv_engine {
                                           (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
             }
             g.cluster = cluster;
+            bd->dual = use_dual && BN == 256 && !g.ups && !g.stride2 && cluster == 1;
             RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN / g.cluster));
             bd->max_clusters = num_sms / g.cluster;
             if (g.cluster > 1) {  // how many clusters of this kernel can be co-resident (GPC boundaries strand SMs)
@@ -552,7 +553,6 @@ struct rfv_engine {
                 q.temb_stride = rc.t ? sumC_ : 0;
                 UmmaGeom g = bd->g;
                 g.m_tiles = (int)(((size_t)rc.B * gHW + 127) / 128);
-                (void)sms;
                 const int super_tiles = ((g.m_tiles + g.cluster - 1) / g.cluster) * g.n_tiles * (g.ups ? 4 : 1);
                 cudaLaunchConfig_t lc{};
                 lc.gridDim = dim3(std::min(super_tiles, bd->max_clusters) * g.cluster);
@@ -563,6 +563,11 @@ struct rfv_engine {
                 at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 lc.attrs = at;
                 lc.numAttrs = g.cluster > 1 ? 1 : 0;
+                if (bd->dual) {   // two M tiles per weight slice (conv_umma_dual_kernel)
+                    const int pairs = ((g.m_tiles + 1) / 2) * g.n_tiles;
+                    conv_umma_dual_kernel<<<std::min(pairs, sms), UMMA_THREADS, UMMA_DUAL_SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                    return cudaGetLastError();
+                }
                 switch (bd->BN) {
                     case 256:
                         lc.dynamicSmemBytes = UmmaCfg<256>::SMEM_BYTES;
@@ -897,6 +902,7 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_DUAL_SMEM_BYTES));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
     std::vector<int> chans(nlev);
@@ -1471,6 +1477,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
     e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
+    e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
     if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {
