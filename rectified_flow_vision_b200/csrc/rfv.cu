@@ -789,7 +789,7 @@ struct rfv_engine {
     // start at koff_base (second source of a shortcut over a virtual concat).
     int bwd_wgrad(const std::string& label, int kind, const ActP& a, const bf16* dy, int Cout, int Wo, int Ho, int pi, int ldw, int koff_base,
                   float* dst_override = nullptr) {
-        struct Bundle { CUtensorMap ma[4], my; WgradGeom g; size_t smem; };
+        struct Bundle { CUtensorMap ma[4], my[4]; WgradGeom g; size_t smem; };
         auto bd = std::make_shared<Bundle>();
         if (a->C % 64 != 0 || Cout % 64 != 0) return fail(RFV_ERR_INVALID, "wgrad %s: channel counts must be multiples of 64", label.c_str());
         if (!make_wgrad_geom(&bd->g, Wo, Ho, a->C, Cout, kind, ldw, koff_base)) return fail(RFV_ERR_INVALID, "wgrad %s: tile does not fit shared memory", label.c_str());
@@ -803,18 +803,27 @@ struct rfv_engine {
                     RFV_TRY(make_map4(&bd->ma[ph * 2 + pw], a->p + ((size_t)ph * a->W + pw) * a->C, a->C, Wo, Ho, cap, (size_t)2 * a->C,
                                       (size_t)2 * a->W * a->C, (size_t)a->H * a->W * a->C, g.pitch, g.R + 2, 1));
         }
-        RFV_TRY(make_map4(&bd->my, dy, Cout, Wo, Ho, cap, Cout, (size_t)Wo * Cout, (size_t)Ho * Wo * Cout, g.pitch, g.R, 1));
+        if (kind != 3) {
+            RFV_TRY(make_map4(&bd->my[0], dy, Cout, Wo, Ho, cap, Cout, (size_t)Wo * Cout, (size_t)Ho * Wo * Cout, g.pitch, g.R, 1));
+            bd->my[1] = bd->my[2] = bd->my[3] = bd->my[0];
+        } else {   // dy is the HIGH-resolution gradient [cap, 2*Ho, 2*Wo, Cout]; variant (py,px) reads its parity view
+            const int Wh = 2 * Wo, Hh = 2 * Ho;
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px)
+                    RFV_TRY(make_map4(&bd->my[py * 2 + px], dy + ((size_t)py * Wh + px) * Cout, Cout, Wo, Ho, cap, (size_t)2 * Cout,
+                                      (size_t)2 * Wh * Cout, (size_t)Hh * Wh * Cout, g.pitch, g.R, 1));
+        }
         bd->smem = wgrad_smem_bytes(g);
         const int taps = kind == 1 ? 1 : 9;
-        const double fl = 2.0 * taps * a->C * Cout * Ho * Wo;
+        const double fl = 2.0 * taps * a->C * Cout * Ho * Wo * (kind == 3 ? 4 : 1);  // algorithmic (kind 3: at the high resolution)
         const int sms = num_sms;
         push("wgrad_umma", "bwd:wgrad:" + label, fl, [this, bd, pi, sms, dst_override](const RunCtx& rc, cudaStream_t s) {
             WgradGeom g = bd->g;
             g.num_tiles = rc.B * g.tiles_per_img;
             const long long total = (long long)g.nvar * g.cchA * g.cchB * g.num_tiles;
             const int grid = (int)std::min<long long>(total, sms);
-            wgrad_umma_kernel<<<grid, WG_THREADS, bd->smem, s>>>(bd->ma[0], bd->ma[1], bd->ma[2], bd->ma[3], bd->my,
-                                                                 dst_override ? dst_override : gslot(pi), g);
+            wgrad_umma_kernel<<<grid, WG_THREADS, bd->smem, s>>>(bd->ma[0], bd->ma[1], bd->ma[2], bd->ma[3], bd->my[0], bd->my[1], bd->my[2],
+                                                                 bd->my[3], dst_override ? dst_override : gslot(pi), g);
             return cudaGetLastError();
         });
         return 0;
@@ -1218,18 +1227,11 @@ int rfv_engine::build() {
                 ConvLayer* gu;
                 RFV_TRY(add_dgrad_layer(&gu, u, 0));
                 begin_bwd();
-                ActP U, T;
+                ActP T;
                 const int Cc = chans[lv], lo = res / 2;
-                RFV_TRY(scratch_act(&U, 0, Cc, res, res));
-                {
-                    const bf16* src = h->p;
-                    bf16* dst = U->p;
-                    push("elementwise_bwd", "bwd:upsample2x:" + u->name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
-                        upsample2x_kernel<<<4096, 256, 0, s>>>(src, dst, rc.B, lo, lo, Cc);
-                        return cudaGetLastError();
-                    });
-                }
-                RFV_TRY(bwd_wgrad(u->name, 0, U, o->grad, Cc, res, res, u->iw, 9 * Cc, 0));
+                // weight gradient in the sub-pixel formulation (four phases x 2x2 taps over the LOW-resolution input; each
+                // pre-summed tap's gradient is added to the 3x3 taps it stands for): 2.25x fewer MACs, nothing materialised
+                RFV_TRY(bwd_wgrad(u->name, 3, h, o->grad, Cc, lo, lo, u->iw, 9 * Cc, 0));
                 bwd_colsum(u->name + ".bias", o->grad, Cc, res * res, nullptr, 0, u->ib, -1);
                 RFV_TRY(scratch_act(&T, 1, Cc, res, res));
                 RFV_TRY(conv_op(gu, grad_view(o), {}, nullptr, T, -1, false));

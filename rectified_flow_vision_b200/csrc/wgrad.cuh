@@ -43,6 +43,9 @@ struct WgradGeom {
     int u_lbo[4][WG_MAX_UNITS];    // bytes from the first to the second atom
     int u_koff0[4][WG_MAX_UNITS];  // gradient column offset of the first / second atom (before + chunk*64 + ci); -1: discard
     int u_koff1[4][WG_MAX_UNITS];
+    int y_per_var;                 // 1: variant v reads its own dY map (sub-pixel phases of an upsample conv)
+    int u_kx0[4][WG_MAX_UNITS][3]; // further gradient columns the first / second atom is ALSO added to (-1: none): a
+    int u_kx1[4][WG_MAX_UNITS][3]; // pre-summed sub-pixel tap is the sum of up to four 3x3 taps, so its gradient goes to each
 };
 
 // Matrix descriptor, MN-major operand, 128-byte swizzle (see header comment).
@@ -59,7 +62,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                  const __grid_constant__ CUtensorMap mapY, float* __restrict__ dW, const WgradGeom g) {
+                  const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapY1,
+                  const __grid_constant__ CUtensorMap mapY2, const __grid_constant__ CUtensorMap mapY3, float* __restrict__ dW,
+                  const WgradGeom g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = g.a_stage_bytes + g.b_stage_bytes;
@@ -105,7 +110,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 mbar_arrive_expect_tx(&full[st], g.a_box_bytes + g.ncob * g.b_box_bytes);
                 const CUtensorMap* ma = var == 0 ? &mapA0 : (var == 1 ? &mapA1 : (var == 2 ? &mapA2 : &mapA3));
                 tma_load_4d(sa + 1024, ma, &full[st], a * 64, -1, r0 - 1, n);
-                for (int j = 0; j < g.ncob; ++j) tma_load_4d(sb + j * g.b_sub_bytes, &mapY, &full[st], (b * g.ncob + j) * 64, -1, r0, n);
+                const CUtensorMap* my = (!g.y_per_var || var == 0) ? &mapY : (var == 1 ? &mapY1 : (var == 2 ? &mapY2 : &mapY3));
+                for (int j = 0; j < g.ncob; ++j) tma_load_4d(sb + j * g.b_sub_bytes, my, &full[st], (b * g.ncob + j) * 64, -1, r0, n);
             }
             __syncwarp();
             if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1; }
@@ -174,6 +180,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         float* dst = dW + (size_t)(b * N + ch * 32) * g.ldw + koff + a * 64 + (row & 63);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * g.ldw, __uint_as_float(acc[j]));
+                        for (int x = 0; x < 3; ++x) {   // sub-pixel atoms: the same values belong to further 3x3 taps
+                            const int kx = row < 64 ? g.u_kx0[var][u][x] : g.u_kx1[var][u][x];
+                            if (kx < 0) break;
+                            float* d2 = dW + (size_t)(b * N + ch * 32) * g.ldw + kx + a * 64 + (row & 63);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(d2 + (size_t)j * g.ldw, __uint_as_float(acc[j]));
+                        }
                     }
                 }
             }
@@ -218,6 +231,9 @@ inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int k
     g->ldw = ldw;
     // atoms (tap shifts) per variant
     int vshift[4][9], vkoff[4][9], vn[4] = {0, 0, 0, 0};
+    int vkx[4][9][3];
+    for (int v = 0; v < 4; ++v)
+        for (int i = 0; i < 9; ++i) vkx[v][i][0] = vkx[v][i][1] = vkx[v][i][2] = -1;
     if (kind == 0) {
         const int split = g->ncob == 2 ? 5 : 9;   // variant 0: taps [0, split), variant 1: the rest
         g->nvar = g->ncob == 2 ? 2 : 1;
@@ -230,6 +246,29 @@ inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int k
     } else if (kind == 1) {
         g->nvar = 1;
         vshift[0][0] = g->pitch; vkoff[0][0] = koff_base; vn[0] = 1;
+    } else if (kind == 3) {
+        // nearest-x2 upsample + 3x3 conv as four sub-pixel phases (W, H: the LOW resolution = grid of each dY parity view):
+        // out[2i+py, 2j+px] = sum_{a,b} W'[py,px][a,b] . in[i+a+py-1, j+b+px-1];  W'[..][a,b] = sum of the 3x3 taps (ky,kx) with
+        // ky in KY(py,a), kx in KX(px,b):  (0,0)->{0} (0,1)->{1,2} (1,0)->{0,1} (1,1)->{2}.  dW[ky,kx] += dW'[phase][a,b].
+        g->nvar = 4;
+        g->y_per_var = 1;
+        for (int var = 0; var < 4; ++var) {
+            const int py = var >> 1, px = var & 1;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    const int i = vn[var]++;
+                    vshift[var][i] = (a + py) * g->pitch + (b + px - 1);
+                    const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+                    const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+                    int cnt = 0;
+                    for (int ky = ky0; ky <= ky1; ++ky)
+                        for (int kx = kx0; kx <= kx1; ++kx) {
+                            const int ko = koff_base + (ky * 3 + kx) * Cin;
+                            if (cnt == 0) vkoff[var][i] = ko; else vkx[var][i][cnt - 1] = ko;
+                            ++cnt;
+                        }
+                }
+        }
     } else {
         // parity view (ph,pw): in[2i+ph, 2j+pw]; tap ky reads row 2i+ky-1: ky=1 -> ph 0 shift 0; ky=0 -> ph 1 shift -1; ky=2 -> ph 1 shift 0
         g->nvar = 4;
@@ -252,8 +291,11 @@ inline bool make_wgrad_geom(WgradGeom* g, int W, int H, int Cin, int Cout, int k
         int nu = 0;
         for (int i = 0; i + 1 < na; i += 2) {
             g->u_shift[var][nu] = shift[i]; g->u_lbo[var][nu] = (shift[i + 1] - shift[i]) * 128;
-            g->u_koff0[var][nu] = koff[i]; g->u_koff1[var][nu] = koff[i + 1]; ++nu;
+            g->u_koff0[var][nu] = koff[i]; g->u_koff1[var][nu] = koff[i + 1];
+            for (int x = 0; x < 3; ++x) { g->u_kx0[var][nu][x] = vkx[var][i][x]; g->u_kx1[var][nu][x] = vkx[var][i + 1][x]; }
+            ++nu;
         }
+        for (int x = 0; x < 3 && (na & 1); ++x) g->u_kx0[var][nu][x] = g->u_kx1[var][nu][x] = -1;   // odd tails: 3x3 / 1x1 only
         if (na & 1) {
             if (na == 1) { g->u_shift[var][nu] = shift[0]; g->u_lbo[var][nu] = 1024; g->u_koff0[var][nu] = koff[0]; g->u_koff1[var][nu] = -1; }
             else { g->u_shift[var][nu] = shift[na - 2]; g->u_lbo[var][nu] = (shift[na - 1] - shift[na - 2]) * 128; g->u_koff0[var][nu] = -1; g->u_koff1[var][nu] = koff[na - 1]; }
