@@ -131,6 +131,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         else if (g.taps == 4) { dy = (tap >> 1) + py - 1; dx = (tap & 1) + px - 1; }
                         if (!g.stride2) {
                             tma_load_4d(sa, &mapA0, &full_bar[stage], cc * 64, w0 + dx, h0 + dy, n0);
+                        } else if (g.taps == 16) {
+                            // data gradient of a nearest-x2-upsample + 3x3 conv: tap = (phase, a, b) reads the parity view
+                            // `phase` of the high-resolution gradient at (i + 1 - a - py, j + 1 - b - px)
+                            const int ph = tap >> 2, a = (tap >> 1) & 1, b = tap & 1;
+                            const CUtensorMap* mp = ph == 0 ? &mapA0 : (ph == 1 ? &mapA1 : (ph == 2 ? &mapA2 : &mapA3));
+                            tma_load_4d(sa, mp, &full_bar[stage], cc * 64, w0 + 1 - b - (ph & 1), h0 + 1 - a - (ph >> 1), n0);
                         } else {
                             // input row 2*ho + dy: dy=-1 -> odd rows at ho-1; dy=0 -> even rows at ho; dy=+1 -> odd rows at ho
                             const int ph = (dy == 0) ? 0 : 1, pw = (dx == 0) ? 0 : 1;

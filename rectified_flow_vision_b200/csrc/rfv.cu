@@ -756,7 +756,8 @@ struct rfv_engine {
 
     // Data-gradient twin of a forward conv: the same kernels on repacked weights.
     // kind 0: segment 0 transposed + spatially flipped (3x3 or 1x1, stride 1); 1: the fused 1x1 shortcut segment
-    // transposed; 2: stride-2 conv as four sub-pixel phases over dY.
+    // transposed; 2: stride-2 conv as four sub-pixel phases over dY; 3: nearest-x2-upsample + 3x3 conv as a 16-tap
+    // stride-2 conv over the four parity views of dY (the adjoint of the sub-pixel forward).
     int add_dgrad_layer(ConvLayer** out, ConvLayer* src, int kind) {
         auto L = std::make_unique<ConvLayer>();
         const int C1 = src->C1a + src->C1b;
@@ -764,7 +765,8 @@ struct rfv_engine {
         L->stride = 1;
         if (kind == 0) { L->C0 = src->Cout; L->Cout = src->C0; L->ks = src->ks; L->K0 = L->ks * L->ks * L->C0; }
         else if (kind == 1) { L->C0 = src->Cout; L->Cout = C1; L->ks = 1; L->K0 = L->C0; }
-        else { L->C0 = src->Cout; L->Cout = src->C0; L->ks = 3; L->ups = 1; L->subpixel = true; L->K0 = 4 * L->C0; }
+        else if (kind == 2) { L->C0 = src->Cout; L->Cout = src->C0; L->ks = 3; L->ups = 1; L->subpixel = true; L->K0 = 4 * L->C0; }
+        else { L->C0 = src->Cout; L->Cout = src->C0; L->ks = 4; L->stride = 2; L->K0 = 16 * L->C0; }  // 3: upsample conv
         L->Ktot = L->K0;
         RFV_TRY(dalloc(&L->w, (size_t)L->Cout * L->Ktot * (L->subpixel ? 4 : 1)));
         L->bias = zero_bias;
@@ -776,7 +778,8 @@ struct rfv_engine {
             if (rc) return rc;
             if (kind == 0) pack_conv_weight_T_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0, src->ks * src->ks, 0, 0);
             else if (kind == 1) pack_conv_weight_T_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, C1, 1, 0, 0);
-            else pack_down_dgrad_weight_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0);
+            else if (kind == 2) pack_down_dgrad_weight_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0);
+            else pack_up_dgrad_weight_kernel<<<256, 256, 0, s>>>(pf(pi), l->w, src->Cout, src->C0);
             return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "dgrad weight pack launch failed");
         };
         *out = l;
@@ -1219,31 +1222,19 @@ int rfv_engine::build() {
             const int ku = h->consumers++;
             RFV_TRY(conv_op(u, h, {}, nullptr, o, -1, true));
             if (train) {
-                // backward of nearest-x2 + conv3x3 (models/unet.py:215-218): the weight gradient sees the materialised
-                // upsampled input; the data gradient is the plain 3x3 transposed conv at the high resolution followed
-                // by the adjoint of the upsample (2x2 sum pool)
+                // backward of nearest-x2 + conv3x3 (models/unet.py:215-218), both in the sub-pixel formulation of the forward:
+                // nothing is upsampled or pooled, 2.25x fewer MACs than the literal high-resolution 3x3
                 RFV_TRY(ensure_grad(o));
                 RFV_TRY(ensure_grad(h));
                 ConvLayer* gu;
-                RFV_TRY(add_dgrad_layer(&gu, u, 0));
+                RFV_TRY(add_dgrad_layer(&gu, u, 3));
                 begin_bwd();
-                ActP T;
                 const int Cc = chans[lv], lo = res / 2;
                 // weight gradient in the sub-pixel formulation (four phases x 2x2 taps over the LOW-resolution input; each
                 // pre-summed tap's gradient is added to the 3x3 taps it stands for): 2.25x fewer MACs, nothing materialised
                 RFV_TRY(bwd_wgrad(u->name, 3, h, o->grad, Cc, lo, lo, u->iw, 9 * Cc, 0));
                 bwd_colsum(u->name + ".bias", o->grad, Cc, res * res, nullptr, 0, u->ib, -1);
-                RFV_TRY(scratch_act(&T, 1, Cc, res, res));
-                RFV_TRY(conv_op(gu, grad_view(o), {}, nullptr, T, -1, false));
-                {
-                    const bf16* src = T->p;
-                    bf16* dst = h->grad;
-                    ActP hh = h;
-                    push("elementwise_bwd", "bwd:sumpool2x2:" + u->name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
-                        sumpool2x2_kernel<<<4096, 256, 0, s>>>(src, dst, rc.B, lo, lo, Cc, ku != hh->consumers - 1 ? 1 : 0);
-                        return cudaGetLastError();
-                    });
-                }
+                RFV_TRY(conv_op(gu, grad_view(o), {}, nullptr, grad_view(h), -1, false, h, ku));
                 end_bwd();
             }
             release(h);

@@ -444,6 +444,24 @@ __global__ void pack_down_dgrad_weight_kernel(const float* __restrict__ src, bf1
         dst[idx] = __float2bfloat16_rn(v);
     }
 }
+// Data gradient of nearest-x2 upsample + 3x3 conv as a 16-tap stride-2 conv over the four parity views of dY:
+// dst[i][((py*2+px)*4 + a*2+b)*O + o] = sum of src[o][i][ky][kx] over ky in KY(py,a), kx in KX(px,b)  (fp32 sum, then bf16)
+__global__ void pack_up_dgrad_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I) {
+    const size_t total = (size_t)16 * O * I;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx % O);
+        const int tap = (int)((idx / O) % 16);
+        const int i = (int)(idx / ((size_t)16 * O));
+        const int py = tap >> 3, px = (tap >> 2) & 1, a = (tap >> 1) & 1, b = tap & 1;
+        const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        const float* w = src + ((size_t)o * I + i) * 9;
+        float acc = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
+        dst[idx] = __float2bfloat16_rn(acc);
+    }
+}
 // Output conv data gradient in the shape input_conv_kernel consumes: wt[(s*9 + t)][c] = W[s][c][8-t], fp32.
 __global__ void pack_output_dgrad_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
