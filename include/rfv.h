@@ -64,6 +64,8 @@ typedef struct {
 #define RFV_FLAG_DUAL      128 /* 256-output-channel convs: share each weight slice between two M tiles (conv_umma_dual_kernel).
                                   Measured on B200 at micro-batch 256: 1.49 ms vs 1.43 ms for the 18 launches -- the lost
                                   epilogue overlap costs more than the halved weight traffic gains; off by default. */
+#define RFV_FLAG_ONE_STREAM 2048 /* training: run the whole backward pass on one stream (default: weight / bias gradients on a
+                                   second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

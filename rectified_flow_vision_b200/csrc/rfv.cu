@@ -111,6 +111,8 @@ struct Op {
     std::string kind;    // kernel class for the profile report
     double flops = 0;    // algorithmic FLOPs per image
     std::function<cudaError_t(const RunCtx&, cudaStream_t)> run;
+    int lane = 0;        // backward pass: 0 = main stream, 1 = side stream (weight / bias gradients)
+    int sync = 0;        // 1: the side stream first waits for everything enqueued on main; 2: main first waits for side
 };
 
 struct ConvLayer {
@@ -197,6 +199,9 @@ struct rfv_engine {
     int n_adam_blocks = 0;
     bool adam_dirty = true;
     cudaGraphExec_t repack_graph = nullptr;
+    cudaStream_t s_bwd = nullptr, s_side = nullptr;
+    cudaEvent_t ev_bwd[4]{};
+    bool two_streams = true;   // RFV_FLAG_ONE_STREAM: run the whole backward pass on one stream (A/B testing)
     int norm_sites = 0;
     struct TimeProj { int off, Cout, iw, ib, icb; };
     std::vector<TimeProj> time_projs;
@@ -218,6 +223,9 @@ struct rfv_engine {
             if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (repack_graph) cudaGraphExecDestroy(repack_graph);
+        for (auto& e : ev_bwd) if (e) cudaEventDestroy(e);
+        if (s_bwd) cudaStreamDestroy(s_bwd);
+        if (s_side) cudaStreamDestroy(s_side);
         if (ev_weights) cudaEventDestroy(ev_weights);
         if (ev_last) cudaEventDestroy(ev_last);
         if (s_h2d) cudaStreamDestroy(s_h2d);
@@ -331,6 +339,11 @@ struct rfv_engine {
               std::function<cudaError_t(const RunCtx&, cudaStream_t)> fn) {
         Op op;
         op.kind = kind; op.label = label; op.flops = flops; op.run = std::move(fn);
+        if (rec != &ops) {
+            op.lane = cur_lane;
+            if (cur_lane == 0 && pending_main_sync) { op.sync = 2; pending_main_sync = false; }
+            if (cur_lane == 1 && pending_side_sync) { op.sync = 1; pending_side_sync = false; }
+        }
         if (rec == &ops) flops_per_image += flops;
         rec->push_back(std::move(op));
     }
@@ -712,17 +725,22 @@ struct rfv_engine {
                 RFV_TRY(add_dgrad_layer(&gs, c2, 1));
                 RFV_TRY(scratch_act(&Tsc, 0, Cin, H, W));
                 RFV_TRY(conv_op(gs, dOut, {}, nullptr, Tsc, -1, false));
+                on_side(false);
                 RFV_TRY(bwd_wgrad(name + ".shortcut", 1, srcs[0], out->grad, Cout, W, H, c2->isw, Cin, 0));
                 if (srcs.size() > 1) RFV_TRY(bwd_wgrad(name + ".shortcut/b", 1, srcs[1], out->grad, Cout, W, H, c2->isw, Cin, srcs[0]->C));
             }
+            on_side(false);
             RFV_TRY(bwd_wgrad(name + ".conv2", 0, a2, out->grad, Cout, W, H, c2->iw, 9 * Cout, 0));
             bwd_colsum(name + ".conv2.bias", out->grad, Cout, H * W, nullptr, 0, c2->ib, c2->isb);
+            on_main();
             RFV_TRY(scratch_act(&Ta2, 1, Cout, H, W));
             RFV_TRY(conv_op(g2, dOut, {}, nullptr, Ta2, -1, false));
             RFV_TRY(scratch_act(&Th, 2, Cout, H, W));
             // also d(time projection)[n][c] = sum over pixels of dh (conv1.bias and time_mlp.1.bias get its batch sum later)
             RFV_TRY(bwd_gn(name + ".norm2", n2, Ta2->p, nullptr, nullptr, 0, 0, Th->p, d_tproj + off, sumC));
+            on_side(true);    // reads dh, which main has just produced
             RFV_TRY(bwd_wgrad(name + ".conv1", 0, a1, Th->p, Cout, W, H, c1->iw, 9 * Cin, 0));
+            on_main();
             RFV_TRY(scratch_act(&Ta1, 1, Cin, H, W));
             RFV_TRY(conv_op(g1, Th, {}, nullptr, Ta1, -1, false));
             RFV_TRY(bwd_gn(name + ".norm1", n1, Ta1->p, Tsc ? Tsc->p : nullptr, Cin == Cout ? out->grad : nullptr, ka, kb));
@@ -733,8 +751,16 @@ struct rfv_engine {
 
 
     // ===== training: backward recording (each forward stage appends one block; blocks run back to front) =====
-    void begin_bwd() { bwd_blocks.emplace_back(); rec = &bwd_blocks.back(); }
-    void end_bwd() { rec = &ops; }
+    // Two streams in the backward pass: data gradients and GroupNorm backward on the main one, weight / bias gradients on a
+    // side one (the tcgen05 wgrad kernel leaves the issue slots and HBM idle, the GroupNorm backward leaves the tensor pipe
+    // idle, and both fit on an SM together).  The first main op of a stage waits for all earlier side work (the scratch
+    // tensors it overwrites may still be read there); a side op waits for main where it consumes what main just produced.
+    int cur_lane = 0;
+    bool pending_main_sync = false, pending_side_sync = false;
+    void begin_bwd() { bwd_blocks.emplace_back(); rec = &bwd_blocks.back(); cur_lane = 0; pending_main_sync = true; pending_side_sync = true; }
+    void end_bwd() { rec = &ops; cur_lane = 0; }
+    void on_side(bool wait_main) { cur_lane = 1; if (wait_main) pending_side_sync = true; }
+    void on_main() { cur_lane = 0; }
     float* gslot(int pi) { return gflat + params[pi].goff; }  // run time only (the flat buffer is allocated after the plan)
 
     int ensure_grad(const ActP& a) {
@@ -1067,6 +1093,7 @@ int rfv_engine::build() {
                     return cudaGetLastError();
                 });
             }
+            on_side(true);
             RFV_TRY(bwd_wgrad("input_conv", 0, xpad, dh, mc, S, S, iw, 9 * 64, 0, wscr));
             push("elementwise_bwd", "bwd:extract:input_conv", 0.0, [=](const RunCtx&, cudaStream_t s) {
                 extract_wgrad_kernel<<<(mc * Cin * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), mc, Cin, 64);
@@ -1104,8 +1131,10 @@ int rfv_engine::build() {
                 ConvLayer* gd;
                 RFV_TRY(add_dgrad_layer(&gd, d, 2));
                 begin_bwd();
+                on_side(false);
                 RFV_TRY(bwd_wgrad(d->name, 2, h, o->grad, chans[lv], res, res, d->iw, 9 * chans[lv], 0));
                 bwd_colsum(d->name + ".bias", o->grad, chans[lv], res * res, nullptr, 0, d->ib, -1);
+                on_main();
                 RFV_TRY(conv_op(gd, grad_view(o), {}, nullptr, grad_view(h), -1, false, h, kd));
                 end_bwd();
             }
@@ -1159,8 +1188,10 @@ int rfv_engine::build() {
             RFV_TRY(add_dgrad_layer(&gq, cq, 0));
             begin_bwd();
             ActP T0, T1, T2;
+            on_side(false);
             RFV_TRY(bwd_wgrad("mid_attn.proj", 1, ao, o2->grad, C, res, res, cp->iw, C, 0));
             bwd_colsum("mid_attn.proj.bias", o2->grad, C, N, nullptr, 0, cp->ib, -1);
+            on_main();
             RFV_TRY(scratch_act(&T0, 0, C, res, res));
             RFV_TRY(conv_op(gp, grad_view(o2), {}, nullptr, T0, -1, false));   // d(attention output)
             RFV_TRY(scratch_act(&T1, 1, 3 * C, res, res));
@@ -1180,8 +1211,10 @@ int rfv_engine::build() {
                     return cudaGetLastError();
                 });
             }
+            on_side(true);    // reads d(qkv), which main has just produced
             RFV_TRY(bwd_wgrad("mid_attn.qkv", 1, hn, T1->p, 3 * C, res, res, cq->iw, C, 0));
             bwd_colsum("mid_attn.qkv.bias", T1->p, 3 * C, N, nullptr, 0, cq->ib, -1);
+            on_main();
             RFV_TRY(scratch_act(&T2, 2, C, res, res));
             RFV_TRY(conv_op(gq, T1, {}, nullptr, T2, -1, false));              // d(normalised input)
             RFV_TRY(bwd_gn("mid_attn.norm", na, T2->p, nullptr, o2->grad, kat, 0));  // + identity path x + h
@@ -1232,8 +1265,10 @@ int rfv_engine::build() {
                 const int Cc = chans[lv], lo = res / 2;
                 // weight gradient in the sub-pixel formulation (four phases x 2x2 taps over the LOW-resolution input; each
                 // pre-summed tap's gradient is added to the 3x3 taps it stands for): 2.25x fewer MACs, nothing materialised
+                on_side(false);
                 RFV_TRY(bwd_wgrad(u->name, 3, h, o->grad, Cc, lo, lo, u->iw, 9 * Cc, 0));
                 bwd_colsum(u->name + ".bias", o->grad, Cc, res * res, nullptr, 0, u->ib, -1);
+                on_main();
                 RFV_TRY(conv_op(gu, grad_view(o), {}, nullptr, grad_view(h), -1, false, h, ku));
                 end_bwd();
             }
@@ -1309,11 +1344,13 @@ int rfv_engine::build() {
                     return cudaGetLastError();
                 });
             }
+            on_side(true);
             RFV_TRY(bwd_wgrad("output_conv.2", 0, a, dvpad->p, 64, S, S, iw, 9 * C, 0, wscr));
             push("elementwise_bwd", "bwd:extract:output_conv.2", 0.0, [=](const RunCtx&, cudaStream_t s) {
                 extract_wgrad_kernel<<<(Co * C * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), Co, C, C);
                 return cudaGetLastError();
             });
+            on_main();
             push("input_conv", "bwd:dgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
                 dim3 grid(S * S / 256, rc.B);
                 switch (Co) {
@@ -1395,6 +1432,13 @@ int rfv_engine::finish_training_setup() {
     RFV_TRY(dalloc(&d_adam_blocks, blocks.size()));
     CU_CHECK(cudaMemcpy(d_adam_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice));
     CU_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    {
+        int least = 0, greatest = 0;
+        CU_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU_CHECK(cudaStreamCreateWithPriority(&s_bwd, cudaStreamNonBlocking, greatest));
+        CU_CHECK(cudaStreamCreateWithPriority(&s_side, cudaStreamNonBlocking, least));
+        for (auto& e : ev_bwd) CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     adam_dirty = true;
     return 0;
 }
@@ -1407,25 +1451,42 @@ static AdamSeg make_seg(const Param& p) {
 }
 
 int rfv_engine::run_backward(const RunCtx& rc, cudaStream_t s) {
-    CU_CHECK(cudaMemsetAsync(cs_arena, 0, cs_used * sizeof(float), s));
-    CU_CHECK(cudaMemsetAsync(d_tproj, 0, (size_t)cap * sumC * sizeof(float), s));
+    // hand over from the caller's stream to the engine's two backward streams (main: high priority, side: low)
+    CU_CHECK(cudaEventRecord(ev_bwd[0], s));
+    CU_CHECK(cudaStreamWaitEvent(s_bwd, ev_bwd[0], 0));
+    CU_CHECK(cudaStreamWaitEvent(s_side, ev_bwd[0], 0));
+    CU_CHECK(cudaMemsetAsync(cs_arena, 0, cs_used * sizeof(float), s_bwd));
+    CU_CHECK(cudaMemsetAsync(d_tproj, 0, (size_t)cap * sumC * sizeof(float), s_bwd));
     for (size_t bi = bwd_blocks.size(); bi-- > 0;) {
         for (auto& op : bwd_blocks[bi]) {
+            cudaStream_t st = (op.lane && two_streams) ? s_side : s_bwd;
+            if (two_streams && (op.sync & 1)) {
+                CU_CHECK(cudaEventRecord(ev_bwd[1], s_bwd));
+                CU_CHECK(cudaStreamWaitEvent(s_side, ev_bwd[1], 0));
+            }
+            if (two_streams && (op.sync & 2)) {
+                CU_CHECK(cudaEventRecord(ev_bwd[2], s_side));
+                CU_CHECK(cudaStreamWaitEvent(s_bwd, ev_bwd[2], 0));
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (profiling) {
                 CU_CHECK(cudaEventCreate(&e0));
                 CU_CHECK(cudaEventCreate(&e1));
-                CU_CHECK(cudaEventRecord(e0, s));
+                CU_CHECK(cudaEventRecord(e0, st));
             }
-            cudaError_t e = op.run(rc, s);
+            cudaError_t e = op.run(rc, st);
             if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "launch of %s failed: %s", op.label.c_str(), cudaGetErrorString(e));
             ++launches;
             if (profiling) {
-                CU_CHECK(cudaEventRecord(e1, s));
+                CU_CHECK(cudaEventRecord(e1, st));
                 bwd_prof.push_back({&op, e0, e1});
             }
         }
     }
+    CU_CHECK(cudaEventRecord(ev_bwd[2], s_side));
+    CU_CHECK(cudaStreamWaitEvent(s_bwd, ev_bwd[2], 0));
+    CU_CHECK(cudaEventRecord(ev_bwd[3], s_bwd));
+    CU_CHECK(cudaStreamWaitEvent(s, ev_bwd[3], 0));
     if (profiling) {
         CU_CHECK(cudaStreamSynchronize(s));
         for (auto& r : bwd_prof) {
@@ -1473,6 +1534,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
     e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
     e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
+    e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
     if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {

@@ -20,9 +20,11 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--flags", type=int, default=0)
     a = ap.parse_args()
     torch.manual_seed(0)
     m = pkg.RectifiedFlowModel(image_size=a.size, device="cuda:0")
+    os.environ["RFV_FLAGS"] = str(a.flags)
     eng = m.velocity_net.train_engine(a.size, "cuda:0", micro_batch=a.mb)
     x0 = torch.randn(a.mb, 3, a.size, a.size, device="cuda:0")
     x1 = torch.randn(a.mb, 3, a.size, a.size, device="cuda:0")
