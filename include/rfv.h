@@ -84,6 +84,8 @@ int rfv_tensor_info(rfv_handle h, int index, char* name_buf, int name_buf_len, i
 int rfv_set_tensor(rfv_handle h, const char* name, const float* dev_ptr, int64_t numel, void* stream);
 /* Read a packed tensor back as fp32 in reference layout (bf16-rounded where the engine stores bf16). */
 int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream);
+/* The engine's fp32 copy of a parameter exactly as uploaded / as last written by rfv_optimizer_step (reference layout). */
+int rfv_get_master(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream);
 
 /* ---- the hot path ------------------------------------------------------------------------------------- */
 /* v = velocity_net(x, t): UNet.forward, models/unet.py:229-275 via BaseFlowModel.forward, models/base_flow.py:91-102.

@@ -1614,6 +1614,17 @@ RFV_EXPORT int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, in
     return 0;
 }
 
+RFV_EXPORT int rfv_get_master(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream) {
+    if (!h || !name || !dev_ptr) return fail(RFV_ERR_INVALID, "null argument");
+    auto it = h->param_index.find(name);
+    if (it == h->param_index.end()) return fail(RFV_ERR_INVALID, "unknown tensor '%s'", name);
+    Param& p = h->params[it->second];
+    if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements", name, (long long)p.numel);
+    if (!p.loaded) return fail(RFV_ERR_STATE, "tensor '%s' not loaded", name);
+    CU_CHECK(cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 static size_t image_elems(rfv_handle h) { return (size_t)h->cfg.in_channels * h->cfg.image_size * h->cfg.image_size; }
 
 RFV_EXPORT int rfv_velocity(rfv_handle h, const float* x, const float* t, float* v, int64_t batch, void* stream) {

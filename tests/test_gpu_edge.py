@@ -80,3 +80,24 @@ def test_pair_generation_full_job_shard_is_deterministic():
     assert torch.equal(a0, b0) and a1.device.type == "cpu" and a1.dtype == torch.float32
     assert util.rel_l2(a1.numpy(), b1.numpy()) < 2e-2
     assert torch.equal(a0, torch.randn(40, 3, 32, 32, generator=torch.Generator().manual_seed(42)))
+
+
+def test_two_lane_sampling_matches_single_lane(monkeypatch):
+    """Batches larger than one micro-batch are split over two native handles / streams / host threads; rows are
+    independent, so the result must not depend on the split (RFV_LANES=1 forces the single-lane path)."""
+    from rectified_flow_vision_b200 import engine as E
+    m = _model()
+    x = torch.randn(20, 3, 32, 32, generator=torch.Generator().manual_seed(21)).cuda()
+    two = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=4)
+    two.sync_weights(m.velocity_net)
+    a, _ = two.euler_sample(x, 3)
+    assert two.h2 is not None                                   # the second lane was created and used
+    monkeypatch.setenv("RFV_LANES", "1")
+    one = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=4)
+    one.sync_weights(m.velocity_net)
+    b, _ = one.euler_sample(x, 3)
+    assert one.h2 is None
+    assert util.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-2
+    host = x.cpu().pin_memory()
+    ha = two.euler_sample_host(host, 3)
+    assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
