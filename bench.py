@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 
 IMAGE, CH, EULER_STEPS, TOTAL_PAIRS = 64, 3, 100, 65536
 FLOPS_PER_IMG_STEP = 12.7636e9  # SURVEY.md §8d / BASELINE.md §3 (algorithmic, 64x64)
+# DRAM bytes (read + write) of the 16 conv_halo launches of one velocity evaluation, from the `ncu --set full` capture in
+# profiles/r1b_ncu_forward_full.md (micro-batch 256: 4199 MB) -> per image; the bench scales it to its micro-batch.
+NCU_CONV_HALO_DRAM_BYTES_PER_IMAGE = 4199e6 / 256
+GN_ELEMS_PER_IMAGE = 5013504    # elements normalised per velocity evaluation (30 GroupNorm sites)
 
 
 def peaks():
@@ -338,9 +342,19 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "kernel": names[dom],
                                 "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
                                 "frac_of_burst": ach / pk["burst"], "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                                "traffic": None, "flops_per_forward": fl, "ms_per_forward": tc[dom]["ms"],
+                                "traffic": (NCU_CONV_HALO_DRAM_BYTES_PER_IMAGE * mb if dom == "conv_halo" else None),
+                                "traffic_note": "DRAM read+write bytes of this kernel class per forward from the committed ncu --set full capture "
+                                                "(profiles/r1b_ncu_forward_full.md), scaled from micro-batch 256 to this run's micro-batch",
+                                "flops_per_forward": fl, "ms_per_forward": tc[dom]["ms"],
                                 "all_tcgen05_convs": {"achieved": ach_all, "frac": ach_all / pk["sustained"],
                                                       "frac_of_burst": ach_all / pk["burst"]}}
+        if "gn_apply" in kinds:
+            # second-largest kernel class, HBM-bound: algorithmic bytes = elements x (2 B read + 2 B written)
+            gb = GN_ELEMS_PER_IMAGE * 4.0 * mb
+            ach = gb / (kinds["gn_apply"]["ms"] / 1e3) / 1e9
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm + SiLU + virtual concat, 30 launches of one forward)",
+                                    "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                                    "peak_source": pk["source"], "bytes_per_forward": gb, "ms_per_forward": kinds["gn_apply"]["ms"]}
         # ---- sampling throughput, configs[0] (B=64) and configs[2] (B=4096) ----
         samp = {}
         for bsz, reps in ((64, 5), (4096, 2)):
