@@ -66,6 +66,10 @@ typedef struct {
                                   epilogue overlap costs more than the halved weight traffic gains; off by default. */
 #define RFV_FLAG_ONE_STREAM 2048 /* training: run the whole backward pass on one stream (default: weight / bias gradients on a
                                    second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
+#define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh) instead of a
+                                   separate gn_apply pass.  Correct (parity suite passes), but measured SLOWER on B200 at micro-batch
+                                   256: forward 5.05 -> 6.81 ms -- four transform warps cannot keep up with the MMA stream (2 MUFU
+                                   ops per element on a 2.5x halo-redundant box); off by default. */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

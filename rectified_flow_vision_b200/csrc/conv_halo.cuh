@@ -39,6 +39,7 @@ struct HaloGeom {
     int a_stages, b_stages;
     int resident_b;            // whole weight matrix lives in shared memory
     int base_offset_mode;      // 0 (default, correct on B200): base offset 0; 1: (addr >> 7) & 7 (experiment, wrong)
+    int cch0a;                 // fused-GroupNorm kernel: segment-0 chunks [0, cch0a) come from map A0, the rest from A0b
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, int mode) {

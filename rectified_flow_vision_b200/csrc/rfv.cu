@@ -24,6 +24,7 @@
 #include "conv_params.h"
 #include "conv_halo.cuh"
 #include "conv_halo_pair.cuh"
+#include "conv_halo_fused.cuh"
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
@@ -138,7 +139,7 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false;
+    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false, use_fuse = false;
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
@@ -376,8 +377,13 @@ struct rfv_engine {
     // acc_of / acc_k (training, gradient-producing convs): accumulate into `out` in place unless this is the first
     // backward writer of acc_of's gradient, i.e. the last forward consumer (decided at run time: consumer counts are
     // final only once the whole plan is built).
+    struct FuseReq { const float* coef; int C; int silu; ActP second; };   // GroupNorm applied to segment 0 inside the conv
+    // can this conv take its GroupNorm(+SiLU) inside the kernel?  (halo-reuse geometry, sampling engines only)
+    bool can_fuse_gn(int C0, int Cout, int H, int W) const {
+        return use_fuse && !train && use_umma && use_halo && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
+    }
     int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats,
-                ActP acc_of = nullptr, int acc_k = 0) {
+                ActP acc_of = nullptr, int acc_k = 0, const FuseReq* fr = nullptr) {
         const std::string pre = rec == &ops ? "conv:" : "bwd:dgrad:";
         ConvParams p{};
         p.out = out->p; p.a0 = in0->p;
@@ -405,7 +411,61 @@ struct rfv_engine {
         if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
         const bool halo_ok = umma_ok && use_halo && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
                              (out->W == 32 || out->W == 64 || out->W == 128);
-        if (halo_ok && use_pair && L->Cout % 128 != 0 && (L->C0 >= 128 || L->Cout > 64)) {
+        if (fr) {
+            // halo-reuse kernel with GroupNorm(+SiLU) applied to the segment-0 chunks in shared memory (conv_halo_fused.cuh)
+            if (!halo_ok) return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
+            struct FBundle { CUtensorMap a0, a0b, a1, a2, w; HaloGeom g; int BN; size_t smem; };
+            auto bd = std::make_shared<FBundle>();
+            HaloGeom& g = bd->g;
+            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
+            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
+            g.tiles_per_img = (g.H * g.pitch + 127) / 128;
+            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+            g.cch0a = in0->C / 64;
+            const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
+            bd->BN = BN;
+            g.n_tiles = L->Cout / BN;
+            g.a_box_bytes = g.rows * g.pitch * 128;
+            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
+            g.base_offset_mode = 0;
+            const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
+            const int avail = 227 * 1024 - 2048 - 512;
+            const int bbytes = BN * 128;
+            g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
+            int bregion;
+            if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
+            else { g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8); bregion = g.b_stages * bbytes; }
+            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) { g.resident_b = 0; g.b_stages = 8; bregion = g.b_stages * bbytes; }
+            while (!g.resident_b && g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
+            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
+            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
+            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 512;
+            auto amap = [&](CUtensorMap* m, const ActP& t) {
+                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
+            };
+            RFV_TRY(amap(&bd->a0, in0));
+            bd->a0b = bd->a0; bd->a1 = bd->a0; bd->a2 = bd->a0;
+            if (fr->second) RFV_TRY(amap(&bd->a0b, fr->second));
+            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
+            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            p.gn_coef = fr->coef; p.gn_C = fr->C; p.gn_silu = fr->silu;
+            const int sms = num_sms, sumC_ = sumC;
+            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
+                ConvParams q = p;
+                q.B = rc.B;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                HaloGeom g = bd->g;
+                g.m_tiles = rc.B * g.tiles_per_img;
+                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
+                switch (bd->BN) {
+                    case 256: conv_halo_fused_kernel<256><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g); break;
+                    case 128: conv_halo_fused_kernel<128><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g); break;
+                    default: conv_halo_fused_kernel<64><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g);
+                }
+                return cudaGetLastError();
+            });
+        } else if (halo_ok && use_pair && L->Cout % 128 != 0 && (L->C0 >= 128 || L->Cout > 64)) {
             // 64-output-channel tiles: two taps per MMA (conv_halo_pair.cuh)
             struct PBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; size_t smem; };
             auto bd = std::make_shared<PBundle>();
@@ -662,6 +722,29 @@ struct rfv_engine {
         return 0;
     }
 
+    // GroupNorm site whose apply pass is fused into the consuming conv: registers the affine parameters (same order as gn_op)
+    // and records the tiny per-(image, channel) coefficient kernel.
+    int gn_coef_op(const std::string& name, std::vector<ActP> srcs, int HW, float** coef_out) {
+        int ig, ib, C = 0;
+        for (auto& a : srcs) C += a->C;
+        RFV_TRY(add_param(name + ".weight", C, &ig));
+        RFV_TRY(add_param(name + ".bias", C, &ib));
+        ++norm_sites;
+        float* coef = nullptr;
+        RFV_TRY(dalloc(&coef, (size_t)cap * C * 2));
+        const float* sa = srcs[0]->stats;
+        const float* sb = srcs.size() > 1 ? srcs[1]->stats : nullptr;
+        if (!sa || (srcs.size() > 1 && !sb)) return fail(RFV_ERR_STATE, "gn %s: source without statistics", name.c_str());
+        const int Ca = srcs[0]->C, Cb = srcs.size() > 1 ? srcs[1]->C : 0, ss = slab_shift;
+        const float *gam = pf(ig), *bet = pf(ib);
+        push("gn_coef", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+            gn_coef_kernel<<<rc.B, 256, 0, s>>>(sa, sb, gam, bet, coef, Ca, Cb, HW, ss, 1e-5f);
+            return cudaGetLastError();
+        });
+        *coef_out = coef;
+        return 0;
+    }
+
     // ResidualBlock (models/unet.py:55-64).  srcs: 1 tensor, or 2 for the decoder's virtual concat [h, skip].
     int res_block(const std::string& name, std::vector<ActP> srcs, int Cout, int* temb_cursor, ActP* result) {
         int Cin = 0;
@@ -670,8 +753,13 @@ struct rfv_engine {
         ActP a1, h, a2, out;
         NormSite n1, n2;
         const int ka = srcs[0]->consumers++, kb = srcs.size() > 1 ? srcs[1]->consumers++ : 0;
-        RFV_TRY(new_act(&a1, Cin, H, W, false));
-        RFV_TRY(gn_op(name + ".norm1", srcs, a1, true, false, &n1));
+        const bool fuse1 = can_fuse_gn(Cin, Cout, H, W), fuse2 = can_fuse_gn(Cout, Cout, H, W);
+        float* coef1 = nullptr;
+        if (fuse1) RFV_TRY(gn_coef_op(name + ".norm1", srcs, H * W, &coef1));
+        else {
+            RFV_TRY(new_act(&a1, Cin, H, W, false));
+            RFV_TRY(gn_op(name + ".norm1", srcs, a1, true, false, &n1));
+        }
         ConvLayer *c1, *c2;
         RFV_TRY(add_conv(&c1, name + ".conv1", Cin, Cout, 3, 1, 0, "", 0, 0));
         RFV_TRY(new_act(&h, Cout, H, W, true));
@@ -697,20 +785,32 @@ struct rfv_engine {
             auto prev = params[icb].repack;
             params[icb].repack = [prev, fuse](cudaStream_t s) { int rc = prev ? prev(s) : 0; return rc ? rc : fuse(s); };
         }
-        RFV_TRY(conv_op(c1, a1, {}, nullptr, h, off, true));
-        release(a1);
-        RFV_TRY(new_act(&a2, Cout, H, W, false));
-        RFV_TRY(gn_op(name + ".norm2", {h}, a2, true, true, &n2));  // nn.Dropout follows this SiLU (models/unet.py:62)
-        release(h);
+        if (fuse1) {
+            FuseReq fr{coef1, Cin, 1, srcs.size() > 1 ? srcs[1] : nullptr};
+            RFV_TRY(conv_op(c1, srcs[0], {}, nullptr, h, off, true, nullptr, 0, &fr));
+        } else {
+            RFV_TRY(conv_op(c1, a1, {}, nullptr, h, off, true));
+            release(a1);
+        }
+        float* coef2 = nullptr;
+        if (fuse2) RFV_TRY(gn_coef_op(name + ".norm2", {h}, H * W, &coef2));
+        else {
+            RFV_TRY(new_act(&a2, Cout, H, W, false));
+            RFV_TRY(gn_op(name + ".norm2", {h}, a2, true, true, &n2));  // nn.Dropout follows this SiLU (models/unet.py:62)
+        }
+        if (!fuse2) release(h);
         RFV_TRY(new_act(&out, Cout, H, W, true));
         if (Cin != Cout) {
             RFV_TRY(add_conv(&c2, name + ".conv2", Cout, Cout, 3, 1, 0, name + ".shortcut", srcs[0]->C, srcs.size() > 1 ? srcs[1]->C : 0));
-            RFV_TRY(conv_op(c2, a2, srcs, nullptr, out, -1, true));
+            if (fuse2) { FuseReq fr{coef2, Cout, 1, nullptr}; RFV_TRY(conv_op(c2, h, srcs, nullptr, out, -1, true, nullptr, 0, &fr)); }
+            else RFV_TRY(conv_op(c2, a2, srcs, nullptr, out, -1, true));
         } else {
             RFV_TRY(add_conv(&c2, name + ".conv2", Cout, Cout, 3, 1, 0, "", 0, 0));
-            RFV_TRY(conv_op(c2, a2, {}, srcs[0], out, -1, true));
+            if (fuse2) { FuseReq fr{coef2, Cout, 1, nullptr}; RFV_TRY(conv_op(c2, h, {}, srcs[0], out, -1, true, nullptr, 0, &fr)); }
+            else RFV_TRY(conv_op(c2, a2, {}, srcs[0], out, -1, true));
         }
-        release(a2);
+        if (fuse2) release(h);
+        else release(a2);
         named_acts[name] = out;
         *result = out;
         if (train) {
@@ -943,6 +1043,9 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_DUAL_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
     std::vector<int> chans(nlev);
@@ -1535,6 +1638,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
     e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
+    e->use_fuse = (cfg->flags & RFV_FLAG_FUSE_GN) != 0;
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
     if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {
