@@ -99,68 +99,99 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
                                                          const float* __restrict__ tvec, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, bf16* __restrict__ out,
                                                          float* __restrict__ stats, int H, int W, int Cout, int slab_shift) {
+    // One thread = TWO horizontally adjacent output pixels x all C_out channels (16 at a time): the 3x4 input patch per
+    // channel lives in registers and every broadcast weight vector read from shared memory feeds 8 FMAs instead of 4 (the
+    // one-pixel version was bound by the shared-memory pipe: ncu l1tex 89 %, short-scoreboard stalls).
     constexpr int K = CIN * 9;
     extern __shared__ float sm[];
     float* wsm = sm;               // [K][Cout]
     float* bsm = sm + K * Cout;    // [Cout]
     float* st = bsm + Cout;        // [Cout/8][2]
     const int HW = H * W;
-    const int n = blockIdx.y, pix = blockIdx.x * 256 + threadIdx.x;
+    const int n = blockIdx.y, pix = (blockIdx.x * 256 + threadIdx.x) * 2;   // W is even: both pixels are in the same row
     for (int i = threadIdx.x; i < K * Cout; i += 256) wsm[i] = wt[i];
     for (int i = threadIdx.x; i < Cout; i += 256) bsm[i] = bias[i];
     for (int i = threadIdx.x; i < (Cout / 8) * 2; i += 256) st[i] = 0.f;
+    const bool active = pix < HW;   // the last block of a small image may be partly empty
     const int h = pix / W, w = pix - h * W;
     const float tb = (x1 != nullptr) ? tvec[n] : 0.f;
-    float in[K];
+    float in[CIN][3][4];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int kx = 0; kx < 4; ++kx) {
                 const int hh = h + ky - 1, ww = w + kx - 1;
                 float v = 0.f;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                if (active && hh >= 0 && hh < H && ww >= 0 && ww < W) {
                     const size_t o = ((size_t)n * CIN + ci) * HW + (size_t)hh * W + ww;
                     v = x[o];
                     if (x1 != nullptr) v = (1.0f - tb) * v + tb * x1[o];
                 }
-                in[ci * 9 + ky * 3 + kx] = v;
+                in[ci][ky][kx] = v;
             }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     bf16* orow = out + ((size_t)n * HW + pix) * Cout;
-    for (int c0 = 0; c0 < Cout; c0 += 32) {
-        float acc[32];
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+        float acc[2][16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = bsm[c0 + j];
+        for (int j = 0; j < 16; ++j) { acc[0][j] = bsm[c0 + j]; acc[1][j] = acc[0][j]; }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float a = in[k];
-            const float4* wr = reinterpret_cast<const float4*>(wsm + k * Cout + c0);
+        for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 w4 = wr[j];
-                acc[4 * j] = fmaf(a, w4.x, acc[4 * j]);
-                acc[4 * j + 1] = fmaf(a, w4.y, acc[4 * j + 1]);
-                acc[4 * j + 2] = fmaf(a, w4.z, acc[4 * j + 2]);
-                acc[4 * j + 3] = fmaf(a, w4.w, acc[4 * j + 3]);
-            }
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float a0 = in[ci][ky][kx], a1 = in[ci][ky][kx + 1];
+                    const float4* wr = reinterpret_cast<const float4*>(wsm + (ci * 9 + ky * 3 + kx) * Cout + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w4 = wr[j];
+                        acc[0][4 * j] = fmaf(a0, w4.x, acc[0][4 * j]);         acc[1][4 * j] = fmaf(a1, w4.x, acc[1][4 * j]);
+                        acc[0][4 * j + 1] = fmaf(a0, w4.y, acc[0][4 * j + 1]); acc[1][4 * j + 1] = fmaf(a1, w4.y, acc[1][4 * j + 1]);
+                        acc[0][4 * j + 2] = fmaf(a0, w4.z, acc[0][4 * j + 2]); acc[1][4 * j + 2] = fmaf(a1, w4.z, acc[1][4 * j + 2]);
+                        acc[0][4 * j + 3] = fmaf(a0, w4.w, acc[0][4 * j + 3]); acc[1][4 * j + 3] = fmaf(a1, w4.w, acc[1][4 * j + 3]);
+                    }
+                }
+#pragma unroll
+        for (int px = 0; px < 2 && active; ++px) {
+            *reinterpret_cast<uint4*>(orow + (size_t)px * Cout + c0) = pack8(acc[px]);
+            *reinterpret_cast<uint4*>(orow + (size_t)px * Cout + c0 + 8) = pack8(acc[px] + 8);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + c0 + j * 8) = pack8(acc + j * 8);
         if (stats) {
-            float t8[8];
+            // 4 partial sums per lane (2 slabs x {sum, sum of squares}) over both pixels; every lane ends up with the warp
+            // total of value ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)
+            float t4[4];
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
+            for (int sl = 0; sl < 2; ++sl) {
                 float s = 0.f, ss = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const float v = acc[sl * 8 + j]; s += v; ss += v * v; }
-                t8[sl * 2] = s;
-                t8[sl * 2 + 1] = ss;
+                for (int j = 0; j < 8; ++j) {
+                    const float v0 = active ? acc[0][sl * 8 + j] : 0.f, v1 = active ? acc[1][sl * 8 + j] : 0.f;
+                    s += v0 + v1;
+                    ss += v0 * v0 + v1 * v1;
+                }
+                t4[sl * 2] = s;
+                t4[sl * 2 + 1] = ss;
             }
-            warp_reduce8(t8, lane);
-            if ((lane & 3) == 0) atomicAdd(&st[((c0 >> 3) + (lane >> 3)) * 2 + ((lane >> 2) & 1)], t8[0]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = (lane & 16) ? t4[i] : t4[i + 2], keep = (lane & 16) ? t4[i + 2] : t4[i];
+                t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            {
+                const float send = (lane & 8) ? t4[0] : t4[1], keep = (lane & 8) ? t4[1] : t4[0];
+                t4[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            t4[0] += __shfl_xor_sync(0xffffffffu, t4[0], 4);
+            t4[0] += __shfl_xor_sync(0xffffffffu, t4[0], 2);
+            t4[0] += __shfl_xor_sync(0xffffffffu, t4[0], 1);
+            if ((lane & 7) == 0) {
+                const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+                atomicAdd(&st[((c0 >> 3) + (idx >> 1)) * 2 + (idx & 1)], t4[0]);
+            }
         }
     }
     if (stats) {

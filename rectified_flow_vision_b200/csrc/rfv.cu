@@ -1167,9 +1167,9 @@ int rfv_engine::build() {
         bf16* o = h->p;
         float* st = h->stats;
         const size_t smem = ((size_t)K * mc + mc + (mc / 8) * 2) * sizeof(float);
-        if ((S * S) % 256 != 0) return fail(RFV_ERR_INVALID, "image_size^2 must be a multiple of 256");
+        if (S % 2 != 0) return fail(RFV_ERR_INVALID, "image_size must be even");
         push("input_conv", "conv:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-            dim3 grid(S * S / 256, rc.B);
+            dim3 grid((S * S + 511) / 512, rc.B);
             switch (Cin) {
                 case 1: input_conv_kernel<1><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
                 case 2: input_conv_kernel<2><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
@@ -1455,7 +1455,7 @@ int rfv_engine::build() {
             });
             on_main();
             push("input_conv", "bwd:dgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
-                dim3 grid(S * S / 256, rc.B);
+                dim3 grid((S * S + 511) / 512, rc.B);
                 switch (Co) {
                     case 1: input_conv_kernel<1><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
                     case 2: input_conv_kernel<2><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
