@@ -118,6 +118,49 @@ def cpu_port_pairs_per_sec(sample_images: int, sample_steps: int, repeats: int =
     return img_steps_per_s / EULER_STEPS, cores, best
 
 
+def torch_eager_gpu_image_steps_per_sec(dev, batch: int = 256, steps: int = 2):
+    """Same-box GPU baseline: the functional-PyTorch port of the reference path run by PyTorch eager / cuDNN on this
+    GPU -- fp32 with TF32 off, fp32 with TF32 on, and bf16 autocast.  A baseline only: nothing of it is on the product path."""
+    import torch
+    from oracle import torch_port
+    import rectified_flow_vision_b200 as pkg
+    torch.manual_seed(0)
+    m = pkg.BaseFlowModel(device="cpu")
+    P = {k: v.detach().to(dev) for k, v in m.state_dict().items()}
+    noise = torch.randn(batch, CH, IMAGE, IMAGE, generator=torch.Generator().manual_seed(7)).to(dev)
+    out = {}
+
+    def run():
+        x = noise
+        dt = 1.0 / steps
+        for i in range(steps):
+            t = torch.full((batch,), i * dt, device=dev)
+            x = x + torch_port.unet_forward(P, x, t) * dt
+        return x
+
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        with torch.device(dev):
+            for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    run()
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(2):
+                        run()
+                    b.record()
+                    torch.cuda.synchronize()
+                out[name] = batch * steps * 2 / (a.elapsed_time(b) / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["unit"] = "image-steps/s"
+    out["sample"] = f"batch {batch} x {steps} Euler steps, oracle/torch_port.py on cuda via PyTorch eager + cuDNN"
+    return out
+
+
 def cpu_train_images_per_sec(batch: int):
     import torch
     from oracle import train_oracle
@@ -380,6 +423,11 @@ def run_ours(args):
                                               "functional-PyTorch fp32 port of the reference path (oracle/torch_port.py)"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)}
+        try:
+            line["torch_eager_gpu_baseline"] = torch_eager_gpu_image_steps_per_sec(dev)
+            line["torch_eager_gpu_baseline"]["ours_image_steps_per_sec"] = value * EULER_STEPS
+        except Exception as ex:  # noqa: BLE001
+            line["torch_eager_gpu_baseline"] = {"error": str(ex)[:200]}
         if train is not None:
             try:   # the training step of the oracle (autograd over the functional port + restated AdamW) on the host cores
                 train["cpu_baseline"] = cpu_train_images_per_sec(8)
