@@ -161,6 +161,50 @@ def torch_eager_gpu_image_steps_per_sec(dev, batch: int = 256, steps: int = 2):
     return out
 
 
+def torch_eager_gpu_train_images_per_sec(dev, batch: int = 256):
+    """Same-box GPU baseline of the training step: the reference's step body (interpolation, forward, mse, backward,
+    clip_grad_norm_(1.0), torch.optim.AdamW) on the functional port, PyTorch eager + cuDNN on this GPU, with TF32 and with
+    bf16 autocast.  Baseline only: nothing of it is on the product path."""
+    import torch
+    from oracle import torch_port
+    import rectified_flow_vision_b200 as pkg
+    torch.manual_seed(0)
+    m = pkg.BaseFlowModel(device="cpu")
+    g = torch.Generator().manual_seed(3)
+    x0, x1, t = (torch.randn(batch, CH, IMAGE, IMAGE, generator=g).to(dev), torch.randn(batch, CH, IMAGE, IMAGE, generator=g).to(dev),
+                 torch.rand(batch, generator=g).to(dev))
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        with torch.device(dev):
+            for name, amp in (("tf32", False), ("bf16_autocast", True)):
+                torch.backends.cuda.matmul.allow_tf32 = True
+                torch.backends.cudnn.allow_tf32 = True
+                P = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in m.state_dict().items()}
+                opt = torch.optim.AdamW(list(P.values()), lr=1e-4)
+                times = []
+                for step in range(4):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    tt = t.view(-1, 1, 1, 1)
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                        pred = torch_port.unet_forward_grad(P, (1 - tt) * x0 + tt * x1, t)
+                        loss = torch.nn.functional.mse_loss(pred.float(), x1 - x0)
+                    opt.zero_grad()
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
+                    opt.step()
+                    torch.cuda.synchronize()
+                    times.append(time.perf_counter() - t0)
+                out[name] = batch / min(times[1:])
+                del P, opt
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["unit"] = "images/s"
+    out["sample"] = f"one optimizer step at batch {batch}: autograd over oracle/torch_port.py + clip_grad_norm_ + torch.optim.AdamW, PyTorch eager on cuda"
+    return out
+
+
 def cpu_train_images_per_sec(batch: int):
     import torch
     from oracle import train_oracle
@@ -433,6 +477,10 @@ def run_ours(args):
                 train["cpu_baseline"] = cpu_train_images_per_sec(8)
             except Exception as ex:  # noqa: BLE001
                 train["cpu_baseline"] = {"value": None, "error": str(ex)}
+            try:
+                train["torch_eager_gpu_baseline"] = torch_eager_gpu_train_images_per_sec(dev)
+            except Exception as ex:  # noqa: BLE001
+                train["torch_eager_gpu_baseline"] = {"error": str(ex)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
