@@ -10,7 +10,9 @@ namespace rfv {
 // ---------------------------------------------------------------------------------------------------------
 // Time embedding: temb_act[b, :] = SiLU(W2 . SiLU(W1 . sincos(t_b) + b1) + b2)        (models/unet.py:20-27,157-162)
 // The trailing SiLU is the first op of every ResidualBlock.time_mlp (models/unet.py:43-46), shared by all blocks.
-// One block per batch row (a single row when t is uniform over the batch, which is the sampling case).
+// grid (rows, TEMB_SLICES): one batch row per blockIdx.x (a single row when t is uniform over the batch, which is the
+// sampling case); the second layer's outputs are split over blockIdx.y, every slice recomputing the small first layer, so
+// that the uniform-t case is not one lonely block on a 148-SM GPU.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, int t_stride_is_zero, float t_scalar,
                                                    const float* __restrict__ w1, const float* __restrict__ b1,
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
         emb[j + half] = cosf(a);
     }
     __syncthreads();
-    if (save_emb)
+    if (save_emb && blockIdx.y == 0)
         for (int j = threadIdx.x; j < mc; j += blockDim.x) save_emb[(size_t)b * mc + j] = emb[j];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int o = warp; o < td; o += nw) {
@@ -42,11 +44,12 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
         s = warp_sum(s);
         if (lane == 0) {
             h1[o] = silu_f(s + b1[o]);
-            if (save_z1) { save_z1[(size_t)b * td + o] = s + b1[o]; save_h1[(size_t)b * td + o] = h1[o]; }
+            if (save_z1 && blockIdx.y == 0) { save_z1[(size_t)b * td + o] = s + b1[o]; save_h1[(size_t)b * td + o] = h1[o]; }
         }
     }
     __syncthreads();
-    for (int o = warp; o < td; o += nw) {
+    const int per = (td + gridDim.y - 1) / gridDim.y, o_lo = blockIdx.y * per, o_hi = min(td, o_lo + per);
+    for (int o = o_lo + warp; o < o_hi; o += nw) {
         float s = 0.f;
         for (int j = lane; j < td; j += 32) s += w2[(size_t)o * td + j] * h1[j];
         s = warp_sum(s);

@@ -1114,7 +1114,7 @@ int rfv_engine::build() {
         push("temb", "temb:time_mlp", 2.0 * (mc * td + td * td), [=](const RunCtx& rc, cudaStream_t s) {
             const int rows = rc.t ? rc.B : 1;
             float *se = rc.train ? temb_emb : nullptr, *s1 = rc.train ? temb_z1 : nullptr, *s2 = rc.train ? temb_z2 : nullptr;
-            temb_kernel<<<rows, 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_, se, s1,
+            temb_kernel<<<dim3(rows, rows >= 64 ? 1 : 8), 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_, se, s1,
                                                                         rc.train ? temb_h1 : nullptr, s2);
             return cudaGetLastError();
         });
