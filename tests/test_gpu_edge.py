@@ -101,3 +101,21 @@ def test_two_lane_sampling_matches_single_lane(monkeypatch):
     host = x.cpu().pin_memory()
     ha = two.euler_sample_host(host, 3)
     assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
+
+
+@pytest.mark.parametrize("flag,name", [(128, "dual M tiles"), (4096, "fused GroupNorm"), (64, "no tap pairing"), (8, "no halo reuse"),
+                                       (512, "cluster-2 weight multicast")])
+def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
+    """The A/B kernels kept behind RFV_FLAG_* (include/rfv.h) compute the same velocity as the default plan."""
+    from rectified_flow_vision_b200 import engine as E
+    m = _model("default64")
+    g = util.golden("default64")
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    outs = []
+    for fl in (0, flag):
+        eng = E.Engine(m.velocity_net.arch(), 64, torch.device("cuda:0"), micro_batch=4, flags=fl)
+        eng.sync_weights(m.velocity_net)
+        outs.append(eng.velocity(x, t).cpu().numpy())
+    assert np.isfinite(outs[1]).all(), name
+    assert util.rel_l2(outs[1], outs[0]) <= 2e-2, (name, util.rel_l2(outs[1], outs[0]))
+    assert util.rel_l2(outs[1], g["v"]) <= 3e-2, name
