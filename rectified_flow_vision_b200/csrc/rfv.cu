@@ -194,7 +194,7 @@ struct rfv_engine {
     size_t scratch_elems = 0;                    // per image
     float *d_tproj = nullptr, *temb_emb = nullptr, *temb_z1 = nullptr, *temb_h1 = nullptr, *temb_z2 = nullptr;
     float *d_tz2 = nullptr, *d_tz1 = nullptr;
-    float *dv_buf = nullptr, *lse = nullptr, *delta = nullptr, *zero_bias = nullptr, *norm2 = nullptr;
+    float *dv_buf = nullptr, *lse = nullptr, *delta = nullptr, *zero_bias = nullptr, *norm2 = nullptr, *norm_partial = nullptr;
     AdamSeg* d_segs = nullptr;
     int2* d_adam_blocks = nullptr;
     int n_adam_blocks = 0;
@@ -1100,6 +1100,7 @@ int rfv_engine::build() {
         RFV_TRY(dalloc(&zero_bias, (size_t)std::max(cmax, 1024)));
         CU_CHECK(cudaMemset(zero_bias, 0, (size_t)std::max(cmax, 1024) * sizeof(float)));
         RFV_TRY(dalloc(&norm2, 1));
+        RFV_TRY(dalloc(&norm_partial, SUMSQ_BLOCKS));
     }
 
     // ---- time embedding (models/unet.py:157-162,231) ----
@@ -1913,8 +1914,8 @@ RFV_EXPORT int rfv_optimizer_step(rfv_handle h, const rfv_adamw* hp, float* grad
         CU_CHECK(cudaStreamSynchronize(s));  // `segs` is a host temporary
         h->adam_dirty = false;
     }
-    CU_CHECK(cudaMemsetAsync(h->norm2, 0, sizeof(float), s));
-    sumsq_kernel<<<1024, 256, 0, s>>>(h->gflat, (size_t)h->gtotal, hp->grad_scale, h->norm2);
+    sumsq_kernel<<<SUMSQ_BLOCKS, 256, 0, s>>>(h->gflat, (size_t)h->gtotal, hp->grad_scale, h->norm_partial);
+    sumsq_final_kernel<<<1, 256, 0, s>>>(h->norm_partial, SUMSQ_BLOCKS, h->norm2);
     CU_CHECK(cudaGetLastError());
     AdamHyper a;
     a.lr = hp->lr; a.beta1 = hp->beta1; a.beta2 = hp->beta2; a.eps = hp->eps; a.wd = hp->weight_decay;

@@ -474,21 +474,35 @@ __global__ void pack_output_dgrad_weight_kernel(const float* __restrict__ src, f
 // ---------------------------------------------------------------------------------------------------------
 // Global-norm clipping + AdamW (torch.nn.utils.clip_grad_norm_(params, 1.0); torch.optim.AdamW defaults)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float scale, float* __restrict__ out) {
-    __shared__ float red[8];
+// Deterministic two-stage sum of squares (fixed grid, fixed summation order): data-parallel replicas must compute the SAME
+// clip coefficient from the same all-reduced gradient or they drift apart bit by bit.
+constexpr int SUMSQ_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float scale, float* __restrict__ partial) {
+    __shared__ float red[256];
     float s = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float v = g[i] * scale;
         s = fmaf(v, v, s);
     }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    red[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-        atomicAdd(out, t);
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
 }
 
 struct AdamSeg {      // one parameter tensor
