@@ -372,6 +372,44 @@ def run_ours(args):
                  "tflops_at_3x_forward": world * tb * 3 * FLOPS_PER_IMG_STEP / (tms / 1e3) / 1e12,
                  "what": "train_rectified_flow step body: x_t interpolation, UNet fwd, MSE, bwd, clip_grad_norm_(1.0), AdamW; "
                          "synthetic N(0,1) pairs, t ~ U[0,1), seeded; gradients all-reduced (SUM) then scaled 1/world"}
+        if rank == 0:
+            # per-kernel-class split of one training step and the rooflines of its dominant tensor / HBM kernels, measured on a
+            # second engine that runs the backward pass on ONE stream (RFV_FLAG_ONE_STREAM): with the production two-stream
+            # schedule the weight-gradient and GroupNorm-backward kernels share the GPU and per-kernel event times overlap
+            from rectified_flow_vision_b200 import engine as _E
+            peng = _E.Engine(tmodel.velocity_net.arch(), IMAGE, dev, micro_batch=min(tb, 256), train=True, flags=2048)
+            peng.sync_weights(tmodel.velocity_net)
+            peng.zero_grad()
+            peng.train_accumulate(tx0, tx1, tt, dropout_p=0.1, seed=1)
+            peng.set_profiling(True)
+            peng.zero_grad()
+            peng.train_accumulate(tx0, tx1, tt, dropout_p=0.1, seed=12345)
+            rep = peng.profile_report()
+            peng.set_profiling(False)
+            del peng
+            ksplit = {}
+            for ln in rep.strip().splitlines():
+                key, ms_tot, n, fl_img = ln.split("\t")
+                kind = key.split(" ", 1)[0] + ("/bwd" if " bwd:" in key else "")
+                k = ksplit.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0})
+                k["ms"] += float(ms_tot)
+                k["launches"] += int(n)
+                k["gflop_per_image"] += float(fl_img) / 1e9
+            train["kernel_split_ms_per_step"] = ksplit
+            pk_ = peaks()
+            if "wgrad_umma/bwd" in ksplit:
+                w = ksplit["wgrad_umma/bwd"]
+                ach = w["gflop_per_image"] * 1e9 * tb / (w["ms"] / 1e3) / 1e12
+                train["roofline"] = {"bound": "tensor", "kernel": "wgrad_umma_kernel (tcgen05 weight gradients, MN-major operands; all launches of one step)",
+                                     "achieved": ach, "peak": pk_["sustained"], "unit": "TFLOP/s", "frac": ach / pk_["sustained"],
+                                     "frac_of_burst": ach / pk_["burst"], "peak_source": pk_["source"], "traffic": None,
+                                     "flops_per_step": w["gflop_per_image"] * 1e9 * tb, "ms_per_step": w["ms"]}
+            if "gn_bwd/bwd" in ksplit:
+                gb = GN_ELEMS_PER_IMAGE * 10.0 * tb   # pass 1 reads 4 B, pass 2 reads 4 B + writes 2 B per element (addends extra)
+                ach = gb / (ksplit["gn_bwd/bwd"]["ms"] / 1e3) / 1e9
+                train["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_bwd_kernel<false/true> (GroupNorm+SiLU+dropout backward, 60 launches of one step)",
+                                         "achieved": ach, "peak": pk_["hbm"], "unit": "GB/s", "frac": ach / pk_["hbm"],
+                                         "bytes_per_step": gb, "ms_per_step": ksplit["gn_bwd/bwd"]["ms"]}
         del tr, tmodel, teng
         torch.cuda.empty_cache()
 
