@@ -211,3 +211,49 @@ def test_training_with_model_channels_128():
             continue
         got = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape)
         assert util.rel_l2(got, gr.numpy()) <= TOL_GRAD_L2, (k, util.rel_l2(got, gr.numpy()))
+
+
+def test_training_curve_tracks_pytorch_autograd():
+    """25 optimizer steps of the native trainer against the same steps through PyTorch fp32 autograd + torch.optim.AdamW on the
+    functional port (same seeded weights and batches, dropout off): the loss curves and the parameter update must agree
+    (tools/check_training_curve.py is the longer version; profiles/r1_training_curve.md its output)."""
+    import rectified_flow_vision_b200 as pkg
+    from rectified_flow_vision_b200.training import NativeTrainer
+    from oracle import torch_port
+    dev, B, LR, STEPS = "cuda:0", 16, 2e-4, 25
+    arch = dict(model_channels=64, channel_mult=(1, 2), num_res_blocks=1)
+    torch.manual_seed(11)
+    m = pkg.RectifiedFlowModel(device=dev, image_size=32, channel_mult=[1, 2], num_res_blocks=1)
+    m.eval()
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    p0 = {k: v.detach().clone() for k, v in P.items()}
+    opt = torch.optim.AdamW(list(P.values()), lr=LR)
+    tr = NativeTrainer(m, lr=LR, micro_batch=B)
+    g = torch.Generator().manual_seed(3)
+    data = torch.tanh(torch.randn(64, 3, 32, 32, generator=g)) * 0.5
+    la, lb = [], []
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        for _ in range(STEPS):
+            idx = torch.randint(0, 64, (B,), generator=g)
+            x1, x0, t = data[idx].to(dev), torch.randn(B, 3, 32, 32, generator=g).to(dev), torch.rand(B, generator=g).to(dev)
+            la.append(float(tr.step(x0, x1, t).item()))
+            tt = t.view(-1, 1, 1, 1)
+            with torch.device(dev):
+                pred = torch_port.unet_forward_grad(P, (1 - tt) * x0 + tt * x1, t, **arch)
+            loss = torch.nn.functional.mse_loss(pred, x1 - x0)
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
+            opt.step()
+            lb.append(float(loss.item()))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    la, lb = np.array(la), np.array(lb)
+    assert np.abs(la - lb).mean() <= 1e-2 * lb.mean(), (la, lb)
+    assert lb[-5:].mean() < lb[:5].mean()
+    sd = dict(m.named_parameters())
+    num = sum(float(((sd[k].detach() - P[k].detach()) ** 2).sum()) for k in P)
+    den = sum(float(((P[k].detach() - p0[k]) ** 2).sum()) for k in P)
+    assert (num / den) ** 0.5 <= 0.15, (num / den) ** 0.5
