@@ -70,6 +70,7 @@ typedef struct {
                                    separate gn_apply pass.  Correct (parity suite passes), but measured SLOWER on B200 at micro-batch
                                    256: forward 5.05 -> 6.81 ms -- four transform warps cannot keep up with the MMA stream (2 MUFU
                                    ops per element on a 2.5x halo-redundant box); off by default. */
+#define RFV_FLAG_NO_ATTN_UMMA 8192 /* attention core on the mma.sync kernel even where the tcgen05 one applies (A/B testing) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

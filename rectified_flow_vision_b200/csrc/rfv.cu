@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "attn.cuh"
+#include "attn_umma.cuh"
 #include "common.cuh"
 #include "conv_mma.cuh"
 #include "conv_params.h"
@@ -1275,9 +1276,20 @@ int rfv_engine::build() {
             const bf16* qp = qkv->p;
             bf16* op = ao->p;
             const float sl2 = (1.0f / std::sqrt((float)d)) * 1.4426950408889634f;
+            // tcgen05 kernel for the default shape (256 tokens, head dim 64); the mma.sync kernel covers the rest
+            const bool au = use_umma && d == 64 && N == 256 && !(cfg.flags & RFV_FLAG_NO_ATTN_UMMA);
+            auto amap = std::make_shared<CUtensorMap>();
+            if (au) {
+                RFV_TRY(make_map2(amap.get(), qkv->p, 3 * C, cap * N, 128));
+                CU_CHECK(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AU_SMEM));
+            }
             push("attention", "attn:mid_attn", 4.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
-                dim3 grid(N / 64, heads, rc.B);
                 float* l = rc.train ? lse : nullptr;
+                if (au) {
+                    attn_umma_kernel<<<dim3(N / 128, heads, rc.B), AU_THREADS, AU_SMEM, s>>>(*amap, op, N, C, sl2, l);
+                    return cudaGetLastError();
+                }
+                dim3 grid(N / 64, heads, rc.B);
                 if (d == 64) attn_kernel<64><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
                 else attn_kernel<32><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
                 return cudaGetLastError();
