@@ -71,6 +71,9 @@ typedef struct {
                                    256: forward 5.05 -> 6.81 ms -- four transform warps cannot keep up with the MMA stream (2 MUFU
                                    ops per element on a 2.5x halo-redundant box); off by default. */
 #define RFV_FLAG_NO_ATTN_UMMA 8192 /* attention core on the mma.sync kernel even where the tcgen05 one applies (A/B testing) */
+#define RFV_FLAG_GN_BWD_TWO_PASS 16384 /* GroupNorm backward as two streaming passes (reduce, apply) everywhere instead of
+                                   the single-pass kernel (A/B testing; the two-pass kernels remain the fallback for pixel counts
+                                   that do not split into equal slices) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -690,7 +690,7 @@ struct rfv_engine {
             site->srcs = srcs; site->ig = ig; site->ib = ib; site->C = C; site->HW = out->H * out->W; site->id = site_id;
             site->silu = silu; site->drop = drop;
             if (train) {
-                const size_t n = (size_t)cap * C * 2;
+                const size_t n = (size_t)cap * C * 2 + cap + 4;   // sums + per-image arrival counters + ticket (gn_bwd_fused_kernel)
                 if (cs_used + n > cs_floats) return fail(RFV_ERR_NOMEM, "GroupNorm-backward arena exhausted");
                 site->cs = cs_arena + cs_used;
                 cs_used += n;
@@ -1010,6 +1010,31 @@ struct rfv_engine {
             q.seed = rc.seed ^ ((uint32_t)id * 0x9E3779B9u);
             q.drop_scale = rc.drop_scale;
         };
+        // Single-pass kernel: smallest number of pixel slices per image whose x + dy fit ~1/3 of an SM's shared memory.
+        // Only for tensors of up to 128 channels: measured at 128 images (B200, one stream) 0.087 ms against 0.132 ms for the
+        // two passes at 64 ch x 64x64, but 0.48 against 0.35 ms on the 192-channel concat (64-pixel slices: the per-CTA
+        // prologue dominates) -- and its 3 x 74 KB of shared memory per SM displaces the weight-gradient kernel of the side
+        // stream, so the whole step (two streams) goes 9.92 -> 9.81 ms with this limit and 9.92 -> 10.24 ms without it.
+        int SL = 0;
+        if (!(cfg.flags & RFV_FLAG_GN_BWD_TWO_PASS) && C <= 128) {
+            for (int c = 1; c <= st.HW / GNF_STAGES; c *= 2) {
+                if (st.HW % (c * GNF_STAGES) != 0) break;
+                if (gn_bwd_fused_smem(C, st.HW / c, threads) <= 75264) { SL = c; break; }   // 3 CTAs per SM
+            }
+        }
+        if (SL) {
+            a.pix_per_block = st.HW / SL;
+            a.arrive = reinterpret_cast<uint32_t*>(st.cs + (size_t)cap * C * 2);
+            a.ticket = a.arrive + cap;
+            const size_t smem = gn_bwd_fused_smem(C, a.pix_per_block, threads);
+            push("gn_bwd", "bwd:gn_fused:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
+                GnBwdArgs q = a;
+                fill(q, rc);
+                gn_bwd_fused_kernel<<<SL * rc.B, threads, smem, s>>>(q, SL);
+                return cudaGetLastError();
+            });
+            return 0;
+        }
         push("gn_bwd", "bwd:gn_reduce:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             GnBwdArgs q = a;
             fill(q, rc);
@@ -1050,6 +1075,7 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (train) CU_CHECK(cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 75264));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
     std::vector<int> chans(nlev);
@@ -1085,7 +1111,7 @@ int rfv_engine::build() {
         scratch_elems = need;
         for (int i = 0; i < 3; ++i) RFV_TRY(dalloc(&scratch[i], (size_t)cap * scratch_elems));
         // one [cap][C][2] slice per norm site: 2 per block (C_in + C_out <= 2 * cmax), attention, output
-        cs_floats = (size_t)cap * 2 * ((size_t)(2 * nlev * nres + 2) * 2 * cmax + 2 * cmax);
+        cs_floats = (size_t)cap * 2 * ((size_t)(2 * nlev * nres + 2) * 2 * cmax + 2 * cmax) + (size_t)(cap + 4) * (4 * nlev * nres + 8);
         RFV_TRY(dalloc(&cs_arena, cs_floats));
         RFV_TRY(dalloc(&d_tproj, (size_t)cap * sumC));
         RFV_TRY(dalloc(&temb_emb, (size_t)cap * mc));

@@ -23,6 +23,21 @@ __device__ __forceinline__ void dropout_mask8(uint32_t seed, uint32_t elem0, uin
     }
 }
 
+// Per-channel block reductions.  Threads are laid out as (pixel lane, channel vector cv = tid % vpp); shared-memory fp32
+// atomicAdd is a compare-and-swap loop (SASS ATOMS.CAST.SPIN), so letting all blockDim / vpp owners of a channel hit the
+// same word costs a 32-way serialised spin for 64 channels.  When vpp divides 32 the lanes of a warp that own the same
+// vector (lane % vpp) are first summed with shuffles; only the first vpp lanes of each warp then touch shared memory.
+// Returns whether this thread still has to publish its values.
+template <int K>
+__device__ __forceinline__ bool warp_sum_same_cv(float* v, int vpp) {
+    if (vpp >= 32 || (32 % vpp) != 0) return true;
+    for (int off = vpp; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    }
+    return (int)(threadIdx.x & 31) < vpp;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GroupNorm(8)(+SiLU)(+dropout) backward over a virtual concat of up to two NHWC bf16 tensors (models/unet.py:56,62,82,224).
 //   y = drop(silu(z)),  z = gamma * xhat + beta,  xhat = (x - mean) * rstd
@@ -39,6 +54,7 @@ struct GnBwdArgs {
     const float* stats_a; const float* stats_b;
     const float* gamma; const float* beta;
     float* cs;                 // [B][C][2]
+    uint32_t* arrive; uint32_t* ticket;   // single-pass kernel: per-image arrival counters [B], work-item ticket
     const bf16* add_cat;       // [B][HW][C]  optional addend in concat layout
     const bf16* add_a;         // [B][HW][Ca] optional addend for source a
     bf16* out_a; bf16* out_b;  // gradient tensors of the sources
@@ -187,20 +203,228 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
         }
     }
     if (!APPLY) {
+        const bool pub_a = warp_sum_same_cv<8>(accA, vpp), pub_b = warp_sum_same_cv<8>(accB, vpp);
+        if (pub_a && pub_b) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sm[(cv * 8 + j) * 2], accA[j]);
-            atomicAdd(&sm[(cv * 8 + j) * 2 + 1], rstd * (accB[j] - mean * accA[j]));   // sum dz*xhat
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sm[(cv * 8 + j) * 2], accA[j]);
+                atomicAdd(&sm[(cv * 8 + j) * 2 + 1], rstd * (accB[j] - mean * accA[j]));   // sum dz*xhat
+            }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.cs + (size_t)n * C * 2 + i, sm[i]);
     } else if (a.out_colsum) {   // dynamic shared memory [C] (the launcher sizes it)
         for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
         __syncthreads();
+        if (warp_sum_same_cv<8>(accA, vpp)) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], accA[j]);
+            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], accA[j]);
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < a.Ca; i += blockDim.x) atomicAdd(a.out_colsum + (size_t)n * a.ld_colsum + i, sm[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Single-pass GroupNorm backward.  An image is cut into SL pixel slices, one CTA each.  A CTA bulk-copies (TMA engine, one
+// mbarrier per stage) its slice of x and dy into shared memory ONCE, reduces its part of the per-channel sums while the later
+// stages are still landing, adds them to the image's totals in cs[n][c][2] (global atomics), and waits on the image's arrival
+// counter until all SL slices have contributed; the second pass (dx) then runs out of shared memory.  x and dy cross HBM once
+// instead of twice (5 tensor passes -> 3) and arrive as asynchronous bulk copies rather than register-held vectors, which is
+// what the two-pass kernels above are latency-bound on.  Slices are ~64 KB so that three CTAs share an SM and the load /
+// reduce / wait / apply phases of different CTAs overlap.
+// Forward progress of the wait: work items are handed out by an atomic ticket, so the SL slices of an image are taken by
+// CTAs that are already running, in start order -- a waiting CTA only ever depends on CTAs that started before it or that
+// start as soon as ANY earlier image (which depends on nothing later) retires.
+// The kernel is instruction-bound (ncu: ~50 % issue-slot use, DRAM < 20 %), so pass 1 writes dz = dy * mask * silu'(z) back
+// over its dy vector in shared memory (bf16, the precision dy itself has) and pass 2 is just dx = dz*k1 + x*k2 + k3; the
+// per-channel sums go through a per-warp table with plain stores instead of shared-memory atomics (CAS loops).
+// Thread mapping and argument block as gn_bwd_kernel (a.pix_per_block = HW / SL; a.arrive / a.ticket are zeroed with cs
+// once per backward pass).  Shared memory: dy slice | xa slice | xb slice | red[rows][2C] | tot[2C] | mbarriers.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GNF_STAGES = 4;
+// rows of the partial-sum table: one per warp (plain stores after warp_sum_same_cv) for up to 128 channels; wider tensors
+// keep one row and add into it with shared-memory atomics (at most blockDim / (C/8) <= 8 owners per word there)
+__host__ __device__ inline int gn_bwd_fused_rows(int C, int threads) {
+    const int vpp = C / 8;
+    return (vpp <= 16 && 32 % vpp == 0) ? threads / 32 : 1;
+}
+__host__ __device__ inline size_t gn_bwd_fused_smem(int C, int np, int threads) {
+    return (size_t)np * C * 4 + (size_t)(gn_bwd_fused_rows(C, threads) + 1) * C * 8 + GNF_STAGES * 8 + 16;
+}
+__global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const GnBwdArgs a, int SL) {
+    extern __shared__ __align__(16) uint8_t gsm[];
+    __shared__ float gmean[8], grstd[8], gS1[8], gS2[8];
+    __shared__ uint32_t s_ticket, s_last;
+    const int C = a.Ca + a.Cb, cpg = C / 8;
+    const int np = a.pix_per_block, ps = np / GNF_STAGES;          // pixels of this CTA / per stage
+    bf16* dys = reinterpret_cast<bf16*>(gsm);
+    bf16* xsa = dys + (size_t)np * C;
+    bf16* xsb = xsa + (size_t)np * a.Ca;
+    const int rows = gn_bwd_fused_rows(C, blockDim.x);
+    float* red = reinterpret_cast<float*>(xsb + (size_t)np * a.Cb);    // [rows][2C] partial sums of this CTA
+    float* tot = red + (size_t)rows * 2 * C;                            // [2C] whole-image sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tot + 2 * C);
+    if (threadIdx.x == 0) {
+        s_ticket = atomicAdd(a.ticket, 1u);
+        for (int s = 0; s < GNF_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    if (rows == 1)
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int n = s_ticket / SL, p0 = (s_ticket % SL) * np;
+    const size_t base = (size_t)n * a.HW + p0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GNF_STAGES; ++s) {
+            const size_t r0 = base + (size_t)s * ps;
+            mbar_arrive_expect_tx(&bars[s], (uint32_t)(ps * C * 4));
+            bulk_load(dys + (size_t)s * ps * C, a.dy + r0 * C, (uint32_t)(ps * C * 2), &bars[s]);
+            bulk_load(xsa + (size_t)s * ps * a.Ca, a.xa + r0 * a.Ca, (uint32_t)(ps * a.Ca * 2), &bars[s]);
+            if (a.Cb) bulk_load(xsb + (size_t)s * ps * a.Cb, a.xb + r0 * a.Cb, (uint32_t)(ps * a.Cb * 2), &bars[s]);
+        }
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 40) gn_group_stats(a, n, threadIdx.x - 32, cpg, &gmean[threadIdx.x - 32], &grstd[threadIdx.x - 32]);
+    __syncthreads();
+    const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
+    const int grp = (cv * 8) / cpg;
+    const float mean = gmean[grp], rstd = grstd[grp];
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = rstd * a.gamma[cv * 8 + j];
+        sh[j] = a.beta[cv * 8 + j] - mean * sc[j];
+    }
+    const bool from_a = cv * 8 < a.Ca;
+    const bf16* xs = from_a ? xsa + cv * 8 : xsb + (cv * 8 - a.Ca);
+    const int cs_ = from_a ? a.Ca : a.Cb;
+    float accA[8], accB[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+    for (int s = 0; s < GNF_STAGES; ++s) {
+        mbar_wait(&bars[s], 0);
+        for (int pp = s * ps + pl; pp < (s + 1) * ps; pp += pstride) {
+            float x[8], dz[8];
+            uint4* dzp = reinterpret_cast<uint4*>(dys + (size_t)pp * C + cv * 8);
+            unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
+            unpack8(*dzp, dz);
+            if (a.drop_thresh) {
+                float mk[8];
+                dropout_mask8(a.seed, (uint32_t)((base + pp) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] *= mk[j];
+            }
+            if (a.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float z = fmaf(x[j], sc[j], sh[j]);
+                    const float sg = sigmoid_fast(z);
+                    dz[j] *= fmaf(z, fmaf(-sg, sg, sg), sg);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { accA[j] += dz[j]; accB[j] = fmaf(dz[j], x[j], accB[j]); }
+            if (a.drop_thresh || a.silu) *dzp = pack8(dz);   // pass 2 reads dz, not dy
+        }
+    }
+    {
+        const bool pub_a = warp_sum_same_cv<8>(accA, vpp), pub_b = warp_sum_same_cv<8>(accB, vpp);
+        if (pub_a && pub_b) {
+            float* dstp = red + (size_t)(rows > 1 ? threadIdx.x >> 5 : 0) * 2 * C + cv * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float va = accA[j], vb = rstd * (accB[j] - mean * accA[j]);   // sum dz, sum dz*xhat
+                if (rows > 1) { dstp[j * 2] = va; dstp[j * 2 + 1] = vb; }
+                else { atomicAdd(dstp + j * 2, va); atomicAdd(dstp + j * 2 + 1, vb); }
+            }
+        }
+    }
+    __syncthreads();
+    float* csn = a.cs + (size_t)n * C * 2;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += red[(size_t)r * 2 * C + i];
+        atomicAdd(csn + i, t);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(a.arrive + n, 1u);
+        s_last = prev == (uint32_t)SL - 1 ? 1u : 0u;
+        if (!s_last) {
+            const volatile uint32_t* flag = a.arrive + n;
+            while (*flag < (uint32_t)SL) __nanosleep(100);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = __ldcg(csn + i);
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int g = threadIdx.x;
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float gm = a.gamma[c];
+            s1 += gm * tot[c * 2];
+            s2 += gm * tot[c * 2 + 1];
+        }
+        const float inv = 1.0f / ((float)cpg * (float)a.HW);
+        gS1[g] = s1 * inv;
+        gS2[g] = s2 * inv;
+    }
+    if (s_last)   // the CTA that completed the image folds its totals into the parameter gradients
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(a.dbeta + c, tot[c * 2]);
+            atomicAdd(a.dgamma + c, tot[c * 2 + 1]);
+        }
+    __syncthreads();
+    const float k2 = -rstd * rstd * gS2[grp], k3 = -rstd * gS1[grp] - mean * k2;   // dx = dz*sc + x*k2 + k3
+    bf16* dst = from_a ? a.out_a + cv * 8 : a.out_b + (cv * 8 - a.Ca);
+    const bool acc = from_a ? a.acc_a != 0 : a.acc_b != 0;
+    const bool has_cat = a.add_cat != nullptr, has_a = a.add_a != nullptr && from_a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accA[j] = 0.f;
+    for (int pp = pl; pp < np; pp += pstride) {
+        uint4 qc, qa, qo;   // optional addends straight from global memory, issued before the arithmetic
+        if (has_cat) qc = *reinterpret_cast<const uint4*>(a.add_cat + (base + pp) * C + cv * 8);
+        if (has_a) qa = *reinterpret_cast<const uint4*>(a.add_a + (base + pp) * a.Ca + cv * 8);
+        if (acc) qo = *reinterpret_cast<const uint4*>(dst + (base + pp) * cs_);
+        float x[8], dz[8], r[8], f[8];
+        unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
+        unpack8(*reinterpret_cast<const uint4*>(dys + (size_t)pp * C + cv * 8), dz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(dz[j], sc[j], fmaf(x[j], k2, k3));
+        if (has_cat) {
+            unpack8(qc, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += f[j];
+        }
+        if (has_a) {
+            unpack8(qa, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += f[j];
+        }
+        if (acc) {
+            unpack8(qo, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += f[j];
+        }
+        if (a.out_colsum) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accA[j] += r[j];
+        }
+        *reinterpret_cast<uint4*>(dst + (base + pp) * cs_) = pack8(r);
+    }
+    if (a.out_colsum) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) tot[i] = 0.f;
+        __syncthreads();
+        if (warp_sum_same_cv<8>(accA, vpp)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&tot[cv * 8 + j], accA[j]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.Ca; i += blockDim.x) atomicAdd(a.out_colsum + (size_t)n * a.ld_colsum + i, tot[i]);
     }
 }
 
@@ -234,7 +458,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
                 for (int j = 0; j < 8; ++j) acc[j] += f[j];
             }
     }
-    if (threadIdx.x < pstride * vpp) {
+    if (warp_sum_same_cv<8>(acc, vpp) && threadIdx.x < pstride * vpp) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], acc[j]);
     }
