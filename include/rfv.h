@@ -74,6 +74,8 @@ typedef struct {
 #define RFV_FLAG_GN_BWD_TWO_PASS 16384 /* GroupNorm backward as two streaming passes (reduce, apply) everywhere instead of
                                    the single-pass kernel (A/B testing; the two-pass kernels remain the fallback for pixel counts
                                    that do not split into equal slices) */
+#define RFV_FLAG_SILU_EXP  32768 /* GroupNorm+SiLU kernel evaluates x / (1 + exp(-x)) (2 MUFU ops) instead of h * (1 + tanh(h)),
+                                   h = x/2 (1 MUFU op, ~2.5e-4 * |h| absolute error); A/B testing */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -265,6 +265,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[cv * 8 + j]; sh[j] = shift[cv * 8 + j]; }
+    // apply_silu == 2: silu(y) = h * (1 + tanh(h)), h = y / 2 -- with the 1/2 folded into scale / shift that is FMA, MUFU.TANH,
+    // FMA per element instead of FMA, FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL (the kernel is issue- and MUFU-bound, not only
+    // HBM-bound).  tanh.approx is good to ~2.5e-4 absolute, i.e. |h| * 2.5e-4 on the result: below bf16 resolution of O(1) values.
+    if (apply_silu == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] *= 0.5f; sh[j] *= 0.5f; }
+    }
     const bool from_a = cv * 8 < Ca;
     const bf16* src = from_a ? xa + cv * 8 : xb + (cv * 8 - Ca);
     const int cs = from_a ? Ca : Cb;
@@ -288,7 +295,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float y = fmaf(f[j], sc[j], sh[j]);
-                    f[j] = apply_silu ? silu_f(y) : y;
+                    if (apply_silu == 2) {
+                        float t;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
+                        f[j] = fmaf(y, t, y);
+                    } else {
+                        f[j] = apply_silu ? silu_f(y) : y;
+                    }
                 }
                 if (drop_thresh) {
                     float mk[8];

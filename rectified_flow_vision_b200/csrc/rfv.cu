@@ -714,12 +714,13 @@ struct rfv_engine {
         if (vpp > 256) return fail(RFV_ERR_INVALID, "gn %s: more than 2048 channels unsupported", name.c_str());
         const int threads = (256 / vpp) * vpp;
         const int sms_ = num_sms;
+        const int silu_mode = (cfg.flags & RFV_FLAG_SILU_EXP) ? 1 : 2;
         push("gn_apply", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             int ppb_run = ppb;   // small batches: smaller pixel slabs so that the grid still fills the GPU (>= 8 blocks per SM)
             while (ppb_run > 64 && ((HW + ppb_run - 1) / ppb_run) * rc.B < 8 * sms_) ppb_run /= 2;
             dim3 grid((HW + ppb_run - 1) / ppb_run, rc.B);
             const uint32_t dt_ = drop ? rc.drop_thresh : 0u;
-            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? 1 : 0, ppb_run, 1e-5f,
+            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? silu_mode : 0, ppb_run, 1e-5f,
                                                                          dt_, rc.seed ^ ((uint32_t)site_id * 0x9E3779B9u), rc.drop_scale);
             return cudaGetLastError();
         });
