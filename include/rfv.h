@@ -76,6 +76,8 @@ typedef struct {
                                    that do not split into equal slices) */
 #define RFV_FLAG_SILU_EXP  32768 /* GroupNorm+SiLU kernel evaluates x / (1 + exp(-x)) (2 MUFU ops) instead of h * (1 + tanh(h)),
                                    h = x/2 (1 MUFU op, ~2.5e-4 * |h| absolute error); A/B testing */
+#define RFV_FLAG_OUTPUT_CONV_TAPS 65536 /* output conv as nine tap-shifted GEMMs (first formulation) instead of one multiply per
+                                   staged pixel followed by a 27-term gather; A/B testing */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

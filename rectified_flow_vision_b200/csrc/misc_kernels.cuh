@@ -431,6 +431,135 @@ __global__ void __launch_bounds__(256) output_conv_kernel(const bf16* __restrict
         }
     }
 }
+// ---------------------------------------------------------------------------------------------------------
+// Output conv, second formulation (C_out <= 3, C = 16*KS): instead of shifting the A operand once per tap (nine ldmatrix
+// passes over the staged tile), every staged pixel is multiplied ONCE by all 9*C_out (<= 27, padded to 32) weight columns:
+//   Z[q][tap*C_out + co] = sum_c a[q][c] * W[co][c][tap]          (mma.sync m16n8k16, B fragments live in registers)
+//   out[p][co]           = bias[co] + sum_tap Z[p + shift(tap)][tap*C_out + co]      (27 shared-memory reads per pixel)
+// Shared-memory traffic per 8x32 tile drops from ~370 KB to ~120 KB (the first formulation is bound by exactly that), and
+// the MMA count from 576 to 352.  Same modes / epilogue as output_conv_kernel.  One tile buffer per block, two blocks per SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OZ_PIX = (OC_TH + 2) * (OC_TW + 2);        // 340 staged pixels
+constexpr int OZ_ROWS = ((OZ_PIX + 15) / 16) * 16;       // 352: whole m16 tiles
+constexpr int OZ_ZP = 29;                                // Z row pitch in floats (odd: conflict-free gathers)
+__host__ __device__ inline size_t output_conv_z_smem(int C) { return (size_t)OZ_ROWS * (C * 2 + 16) + (size_t)OZ_ROWS * OZ_ZP * 4; }
+template <int KS>
+__global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __restrict__ a, const bf16* __restrict__ wpk,
+                                                               const float* __restrict__ bias, float* __restrict__ xv,
+                                                               float* __restrict__ traj, const float* __restrict__ x0,
+                                                               const float* __restrict__ x1, float* __restrict__ mse_acc,
+                                                               int H, int W, int Cout, int B, int mode, float dt) {
+    constexpr int C = KS * 16;
+    constexpr int pitch = C * 2 + 16;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint8_t* tile = smraw;                                               // [OZ_ROWS][pitch] bf16 (rows >= 340 never staged / used)
+    float* Zs = reinterpret_cast<float*>(smraw + (size_t)OZ_ROWS * pitch);   // [OZ_ROWS][OZ_ZP]
+    __shared__ float red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int tw = (W + OC_TW - 1) / OC_TW, th = (H + OC_TH - 1) / OC_TH;
+    const int ntiles = tw * th * B;
+    const int NC = 9 * Cout;                                             // used Z columns
+    // B fragments: column n = tap*Cout + co of the [C x 32] weight matrix, rows k = channels.  wpk is [tap][8][C].
+    uint32_t bf[KS][4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int n = nt * 8 + g;
+        const bool ok = n < NC;
+        const int tap = ok ? n / Cout : 0, co = ok ? n - tap * Cout : 0;
+        const bf16* wr = wpk + (size_t)(tap * 8 + co) * C;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            bf[ks][nt][0] = ok ? *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 2 * tq) : 0u;
+            bf[ks][nt][1] = ok ? *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 2 * tq + 8) : 0u;
+        }
+    }
+    float bco[3];
+#pragma unroll
+    for (int co = 0; co < 3; ++co) bco[co] = co < Cout ? bias[co] : 0.f;
+    constexpr int vec = C >> 3;
+    float sq = 0.f;
+    for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const int n = tile_i / (tw * th), r = tile_i - n * (tw * th);
+        const int h0 = (r / tw) * OC_TH, w0 = (r - (r / tw) * tw) * OC_TW;
+        for (int i = tid; i < OZ_PIX * vec; i += 256) {
+            const int pp = i / vec, cv = i - pp * vec;
+            const int hh = h0 + pp / (OC_TW + 2) - 1, ww = w0 + pp % (OC_TW + 2) - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const bf16* src = ok ? a + (((size_t)n * H + hh) * W + ww) * C + cv * 8 : a;
+            cp_async16(smem_u32(tile + pp * pitch + cv * 16), src, ok);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // Z = tile x W for every staged pixel: m16 tiles mt = warp, warp + 8, ...
+        for (int mt = warp; mt < OZ_ROWS / 16; mt += 8) {
+            float acc[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+            const uint8_t* arow = tile + (mt * 16 + (lane & 15)) * pitch + (lane >> 4) * 16;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t af[4];
+                ldmatrix_x4(smem_u32(arow + ks * 32), af[0], af[1], af[2], af[3]);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], af, bf[ks][nt][0], bf[ks][nt][1]);
+            }
+            float* z0 = Zs + (mt * 16 + g) * OZ_ZP, * z1 = z0 + 8 * OZ_ZP;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int c = nt * 8 + 2 * tq;
+                if (c < NC) { z0[c] = acc[nt][0]; z1[c] = acc[nt][2]; }
+                if (c + 1 < NC) { z0[c + 1] = acc[nt][1]; z1[c + 1] = acc[nt][3]; }
+            }
+        }
+        __syncthreads();
+        // gather: thread = output pixel (row tid / 32, column tid % 32) of the 8x32 tile
+        {
+            const int pr = tid >> 5, pc = tid & 31;
+            const int h = h0 + pr, w = w0 + pc;
+            if (h < H && w < W) {
+                float o[3] = {bco[0], bco[1], bco[2]};
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float* z = Zs + ((pr + tap / 3) * (OC_TW + 2) + pc + tap % 3) * OZ_ZP + tap * Cout;
+#pragma unroll
+                    for (int co = 0; co < 3; ++co)
+                        if (co < Cout) o[co] += z[co];
+                }
+#pragma unroll
+                for (int co = 0; co < 3; ++co) {
+                    if (co < Cout) {
+                        const float val = o[co];
+                        const size_t oi = (((size_t)n * Cout + co) * H + h) * W + w;
+                        if (mse_acc) { const float d = val - (x1[oi] - x0[oi]); sq += d * d; }
+                        if (mode == 0) xv[oi] = val;
+                        else if (mode == 3) xv[oi] = (val - (x1[oi] - x0[oi])) * dt;
+                        else if (mode == 1) {
+                            const float nx = xv[oi] + val * dt;
+                            xv[oi] = nx;
+                            if (traj) traj[oi] = nx;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // tile and Z are rewritten by the next iteration
+    }
+    if (mse_acc) {
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += red[i];
+            atomicAdd(mse_acc, t);
+        }
+    }
+}
+
 // OIHW fp32 [co][c][3][3] -> bf16 [tap][8][C] (rows co >= Cout are zero): the B operand of output_conv_kernel
 __global__ void pack_output_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

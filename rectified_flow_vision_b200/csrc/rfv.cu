@@ -1450,9 +1450,23 @@ int rfv_engine::build() {
         if (smem > 227 * 1024) return fail(RFV_ERR_INVALID, "output conv: %d channels do not fit the shared-memory tile", C);
         CU_CHECK(cudaFuncSetAttribute(output_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int sms = num_sms;
+        // multiply-once formulation where it applies (C_out <= 3, 32 / 64 / 128 channels)
+        const bool oz = Co <= 3 && (C == 32 || C == 64 || C == 128) && !(cfg.flags & RFV_FLAG_OUTPUT_CONV_TAPS);
+        const size_t zsmem = output_conv_z_smem(C);
+        if (oz) {
+            CU_CHECK(cudaFuncSetAttribute(output_conv_z_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)output_conv_z_smem(32)));
+            CU_CHECK(cudaFuncSetAttribute(output_conv_z_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)output_conv_z_smem(64)));
+            CU_CHECK(cudaFuncSetAttribute(output_conv_z_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)output_conv_z_smem(128)));
+        }
         push("output_conv", "conv:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
             const int ntiles = ((S + OC_TW - 1) / OC_TW) * ((S + OC_TH - 1) / OC_TH) * rc.B;
             const int grid = std::min(ntiles, 2 * sms);
+            if (oz) {
+                if (C == 32) output_conv_z_kernel<2><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
+                else if (C == 64) output_conv_z_kernel<4><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
+                else output_conv_z_kernel<8><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
+                return cudaGetLastError();
+            }
             output_conv_kernel<<<grid, 256, smem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.B, rc.mode, rc.dt);
             return cudaGetLastError();
         });
