@@ -78,6 +78,8 @@ typedef struct {
                                    h = x/2 (1 MUFU op, ~2.5e-4 * |h| absolute error); A/B testing */
 #define RFV_FLAG_OUTPUT_CONV_TAPS 65536 /* output conv as nine tap-shifted GEMMs (first formulation) instead of one multiply per
                                    staged pixel followed by a 27-term gather; A/B testing */
+#define RFV_FLAG_INPUT_CONV_FMA 131072 /* input conv on the fp32 FMA pipe (fp32 x and weights) instead of mma.sync with bf16
+                                   operands; A/B testing */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -220,8 +220,8 @@ def unet_forward(P: Dict[str, np.ndarray], x: np.ndarray, t: np.ndarray, spec: O
         if taps is not None:
             taps[name] = val
 
-    # the input conv runs on CUDA cores with fp32 weights; only its output is rounded
-    h_full = conv2d(x, P[pre + "input_conv.weight"], P[pre + "input_conv.bias"], 1, 1)
+    # the input conv runs on the tensor cores too: x and its weights are rounded to bf16 on the way into the MMA
+    h_full = conv2d(pol.act(x), pol.w(P[pre + "input_conv.weight"]), P[pre + "input_conv.bias"], 1, 1)
     h = pol.act(h_full)
     tap("input_conv", h)
 

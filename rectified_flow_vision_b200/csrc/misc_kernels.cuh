@@ -206,6 +206,170 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
         }
     }
 }
+// ---------------------------------------------------------------------------------------------------------
+// Input conv on the tensor cores (mma.sync m16n8k16, bf16 operands, fp32 accumulation): the FMA version above tops out at
+// ~45 % of the fp32 FMA peak, 5x above the kernel's HBM time.  GEMM per 8x32-pixel tile: M = pixels, K = 9*C_in padded to a
+// multiple of 16, N = C_out in chunks of 8*NTC channels.  The fp32 halo of the tile is staged in shared memory; im2col is a
+// per-thread table of K offsets into it (each A-fragment register is two shared-memory reads and one cvt.bf16x2); the weight
+// fragments of the current channel chunk live in registers.  Same outputs as input_conv_kernel: NHWC bf16 + GroupNorm slab
+// statistics of the fp32 result, optional x_t interpolation.  grid (tile groups, B), IM_TPB tiles per block, warp = tile row.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int IM_TH = 8, IM_TW = 32, IM_XP = 36, IM_TPB = 4;
+template <int CIN, int NTC>
+__global__ void __launch_bounds__(256, 2) input_conv_mma_kernel(const float* __restrict__ x, const float* __restrict__ x1,
+                                                                const float* __restrict__ tvec, const float* __restrict__ wt,
+                                                                const float* __restrict__ bias, bf16* __restrict__ out,
+                                                                float* __restrict__ stats, int H, int W, int Cout, int slab_shift) {
+    constexpr int K = CIN * 9, KS = (K + 15) / 16;
+    extern __shared__ float ism[];
+    float* xs = ism;                                     // [CIN][IM_TH + 2][IM_XP]
+    float* st = ism + CIN * (IM_TH + 2) * IM_XP;         // [Cout >> slab_shift][2]
+    // per-warp output staging [32 pixels][NTC*8 channels] bf16, row pitch +16 B: fragment-order writes and the 16-byte row
+    // reads that follow are both bank-conflict free; rows then leave as full 16-byte vectors (4-byte fragment stores straight
+    // to global memory halve the store efficiency and cost as much as the FMA version's arithmetic)
+    constexpr int OP = NTC * 16 + 16;
+    uint8_t* ostage = reinterpret_cast<uint8_t*>(st + (((Cout >> slab_shift) * 2 + 3) & ~3)) + (size_t)(threadIdx.x >> 5) * 32 * OP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int n = blockIdx.y;
+    const int tw = (W + IM_TW - 1) / IM_TW, th = (H + IM_TH - 1) / IM_TH, tiles_img = tw * th;
+    const int t_begin = blockIdx.x * IM_TPB, t_end = min(tiles_img, t_begin + IM_TPB);
+    const int nslab = Cout >> slab_shift;
+    for (int i = tid; i < nslab * 2; i += 256) st[i] = 0.f;
+    // im2col table: k = s*16 + 2*tq + (j & 1) + 8*(j >> 1)  ->  offset of (ci, ky, kx) in the staged halo; -1: zero padding of K
+    int aoff[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = s * 16 + 2 * tq + (j & 1) + 8 * (j >> 1);
+            const int ci = k / 9, r9 = k - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
+            aoff[s][j] = k < K ? (ci * (IM_TH + 2) + ky) * IM_XP + kx : -1;
+        }
+    const float tb = (x1 != nullptr) ? tvec[n] : 0.f;
+    const size_t HW = (size_t)H * W;
+    for (int c0 = 0; c0 < Cout; c0 += NTC * 8) {
+        // B fragments of this channel chunk: b0 = (W[k0+2tq][n], W[k0+2tq+1][n]), b1 = the same 8 rows further down; n = nt*8 + g
+        uint32_t bfr[KS][NTC][2];
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int nt = 0; nt < NTC; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int k = s * 16 + 2 * tq + 8 * hh, col = c0 + nt * 8 + g;
+                    const float w0 = k < K ? wt[(size_t)k * Cout + col] : 0.f;
+                    const float w1 = k + 1 < K ? wt[(size_t)(k + 1) * Cout + col] : 0.f;
+                    bfr[s][nt][hh] = pack_bf16x2(w0, w1);
+                }
+        float sacc[NTC][2];
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt) { sacc[nt][0] = 0.f; sacc[nt][1] = 0.f; }
+        // the halo of tile t+1 is fetched into registers while tile t is multiplied (a block has no other way to hide the
+        // global-memory latency: two blocks of eight warps per SM)
+        constexpr int NPF = (CIN * (IM_TH + 2) * (IM_TW + 2) + 255) / 256;
+        float pv[NPF];
+        auto fetch = [&](int t) {
+            const int h0 = (t / tw) * IM_TH, w0 = (t - (t / tw) * tw) * IM_TW;
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                const int i = tid + u * 256;
+                const int ci = i / ((IM_TH + 2) * (IM_TW + 2)), r = i - ci * ((IM_TH + 2) * (IM_TW + 2));
+                const int yy = r / (IM_TW + 2), xx = r - yy * (IM_TW + 2);
+                const int hh = h0 + yy - 1, ww = w0 + xx - 1;
+                float v = 0.f;
+                if (ci < CIN && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    const size_t o = ((size_t)n * CIN + ci) * HW + (size_t)hh * W + ww;
+                    v = x[o];
+                    if (x1 != nullptr) v = (1.0f - tb) * v + tb * x1[o];
+                }
+                pv[u] = v;
+            }
+        };
+        if (t_begin < t_end) fetch(t_begin);
+        for (int t = t_begin; t < t_end; ++t) {
+            const int h0 = (t / tw) * IM_TH, w0 = (t - (t / tw) * tw) * IM_TW;
+            __syncthreads();   // previous tile's fragments are built; st[] zeroed
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                const int i = tid + u * 256;
+                const int ci = i / ((IM_TH + 2) * (IM_TW + 2)), r = i - ci * ((IM_TH + 2) * (IM_TW + 2));
+                const int yy = r / (IM_TW + 2), xx = r - yy * (IM_TW + 2);
+                if (ci < CIN) xs[(ci * (IM_TH + 2) + yy) * IM_XP + xx] = pv[u];
+            }
+            __syncthreads();
+            if (t + 1 < t_end) fetch(t + 1);
+            const int h = h0 + warp;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float* xr = xs + warp * IM_XP + m * 16 + g;
+                float acc[NTC][4];
+#pragma unroll
+                for (int nt = 0; nt < NTC; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) {
+                    uint32_t af[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {   // q = (k half) * 2 + (row half): a0 (g, k lo), a1 (g+8, k lo), a2 (g, k hi), a3 (g+8, k hi)
+                        const int j0 = (q >> 1) * 2, ro = (q & 1) * 8;
+                        const float v0 = aoff[s][j0] >= 0 ? xr[aoff[s][j0] + ro] : 0.f;
+                        const float v1 = aoff[s][j0 + 1] >= 0 ? xr[aoff[s][j0 + 1] + ro] : 0.f;
+                        af[q] = pack_bf16x2(v0, v1);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NTC; ++nt) mma_bf16_16816(acc[nt], af, bfr[s][nt][0], bfr[s][nt][1]);
+                }
+                const int wa = w0 + m * 16 + g, wb = wa + 8;
+                const bool va = h < H && wa < W, vb = h < H && wb < W;
+                uint8_t* sa = ostage + (m * 16 + g) * OP + tq * 4;
+                uint8_t* sb = sa + 8 * OP;
+#pragma unroll
+                for (int nt = 0; nt < NTC; ++nt) {
+                    const float b0 = bias[c0 + nt * 8 + 2 * tq], b1 = bias[c0 + nt * 8 + 2 * tq + 1];
+                    const float v0 = acc[nt][0] + b0, v1 = acc[nt][1] + b1, v2 = acc[nt][2] + b0, v3 = acc[nt][3] + b1;
+                    *reinterpret_cast<uint32_t*>(sa + nt * 16) = pack_bf16x2(v0, v1);
+                    *reinterpret_cast<uint32_t*>(sb + nt * 16) = pack_bf16x2(v2, v3);
+                    if (va) {
+                        sacc[nt][0] += v0 + v1;
+                        sacc[nt][1] += v0 * v0 + v1 * v1;
+                    }
+                    if (vb) {
+                        sacc[nt][0] += v2 + v3;
+                        sacc[nt][1] += v2 * v2 + v3 * v3;
+                    }
+                }
+            }
+            __syncwarp();
+            if (h < H) {   // this warp's 32-pixel row: NTC 16-byte vectors per pixel
+#pragma unroll
+                for (int i = 0; i < NTC; ++i) {
+                    const int v = i * 32 + lane, px = v / NTC, ch = v - px * NTC;
+                    if (w0 + px < W)
+                        *reinterpret_cast<uint4*>(out + (((size_t)n * H + h) * W + w0 + px) * Cout + c0 + ch * 8) =
+                            *reinterpret_cast<const uint4*>(ostage + px * OP + ch * 16);
+                }
+            }
+            __syncwarp();
+        }
+        if (stats) {
+#pragma unroll
+            for (int nt = 0; nt < NTC; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float v = sacc[nt][q];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) atomicAdd(&st[((c0 + nt * 8 + 2 * tq) >> slab_shift) * 2 + q], v);   // channel pair -> its slab
+                }
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        for (int i = tid; i < nslab * 2; i += 256) atomicAdd(stats + (size_t)n * nslab * 2 + i, st[i]);
+    }
+}
 // OIHW fp32 -> [ci*9+tap][co] fp32 (the layout input_conv_kernel stages into shared memory)
 __global__ void transpose_input_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int K) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,8 +643,8 @@ __global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __res
     for (int co = 0; co < 3; ++co) bco[co] = co < Cout ? bias[co] : 0.f;
     constexpr int vec = C >> 3;
     float sq = 0.f;
-    for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
-        const int n = tile_i / (tw * th), r = tile_i - n * (tw * th);
+    auto stage_tile = [&](int t) {
+        const int n = t / (tw * th), r = t - n * (tw * th);
         const int h0 = (r / tw) * OC_TH, w0 = (r - (r / tw) * tw) * OC_TW;
         for (int i = tid; i < OZ_PIX * vec; i += 256) {
             const int pp = i / vec, cv = i - pp * vec;
@@ -490,8 +654,13 @@ __global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __res
             cp_async16(smem_u32(tile + pp * pitch + cv * 16), src, ok);
         }
         cp_async_commit();
+    };
+    if ((int)blockIdx.x < ntiles) stage_tile(blockIdx.x);
+    for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const int n = tile_i / (tw * th), r = tile_i - n * (tw * th);
+        const int h0 = (r / tw) * OC_TH, w0 = (r - (r / tw) * tw) * OC_TW;
         cp_async_wait<0>();
-        __syncthreads();
+        __syncthreads();   // tile landed; every thread is past the previous gather (Z may be overwritten)
         // Z = tile x W for every staged pixel: m16 tiles mt = warp, warp + 8, ...
         for (int mt = warp; mt < OZ_ROWS / 16; mt += 8) {
             float acc[4][4];
@@ -516,6 +685,8 @@ __global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __res
             }
         }
         __syncthreads();
+        // the tile buffer is free: fetch the next tile while this one's outputs are gathered from Z
+        if (tile_i + (int)gridDim.x < ntiles) stage_tile(tile_i + gridDim.x);
         // gather: thread = output pixel (row tid / 32, column tid % 32) of the 8x32 tile
         {
             const int pr = tid >> 5, pc = tid & 31;
@@ -546,7 +717,6 @@ __global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __res
                 }
             }
         }
-        __syncthreads();   // tile and Z are rewritten by the next iteration
     }
     if (mse_acc) {
         sq = warp_sum(sq);

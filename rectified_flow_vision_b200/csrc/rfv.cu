@@ -1200,7 +1200,34 @@ int rfv_engine::build() {
         float* st = h->stats;
         const size_t smem = ((size_t)K * mc + mc + (mc / 8) * 2) * sizeof(float);
         if (S % 2 != 0) return fail(RFV_ERR_INVALID, "image_size must be even");
+        // tensor-core version where the channel count splits into 64- (or one 32-) channel chunks
+        const int im_ntc = (mc % 64 == 0) ? 8 : (mc == 32 ? 4 : 0);
+        const bool im = im_ntc != 0 && !(cfg.flags & RFV_FLAG_INPUT_CONV_FMA);
+        const size_t im_smem = ((size_t)Cin * (IM_TH + 2) * IM_XP + (size_t)((((mc >> ss) * 2) + 3) & ~3)) * sizeof(float) +
+                               (size_t)8 * 32 * (im_ntc * 16 + 16);
         push("input_conv", "conv:input_conv", 2.0 * K * mc * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+            if (im) {
+                const int tiles_img = ((S + IM_TW - 1) / IM_TW) * ((S + IM_TH - 1) / IM_TH);
+                dim3 grid((tiles_img + IM_TPB - 1) / IM_TPB, rc.B);
+#define RFV_IM_LAUNCH(CI, NT) input_conv_mma_kernel<CI, NT><<<grid, 256, im_smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss)
+                if (im_ntc == 8) {
+                    switch (Cin) {
+                        case 1: RFV_IM_LAUNCH(1, 8); break;
+                        case 2: RFV_IM_LAUNCH(2, 8); break;
+                        case 3: RFV_IM_LAUNCH(3, 8); break;
+                        default: RFV_IM_LAUNCH(4, 8); break;
+                    }
+                } else {
+                    switch (Cin) {
+                        case 1: RFV_IM_LAUNCH(1, 4); break;
+                        case 2: RFV_IM_LAUNCH(2, 4); break;
+                        case 3: RFV_IM_LAUNCH(3, 4); break;
+                        default: RFV_IM_LAUNCH(4, 4); break;
+                    }
+                }
+#undef RFV_IM_LAUNCH
+                return cudaGetLastError();
+            }
             dim3 grid((S * S + 511) / 512, rc.B);
             switch (Cin) {
                 case 1: input_conv_kernel<1><<<grid, 256, smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss); break;
