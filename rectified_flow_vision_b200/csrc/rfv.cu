@@ -1538,7 +1538,33 @@ int rfv_engine::build() {
                 return cudaGetLastError();
             });
             on_main();
+            const int dg_ntc = (C % 64 == 0) ? 8 : (C == 32 ? 4 : 0);
+            const bool dg_mma = dg_ntc != 0 && !(cfg.flags & RFV_FLAG_INPUT_CONV_FMA);
+            const size_t dg_smem = ((size_t)Co * (IM_TH + 2) * IM_XP + (size_t)((((C >> ss) * 2) + 3) & ~3)) * sizeof(float) +
+                                   (size_t)8 * 32 * (dg_ntc * 16 + 16);
             push("input_conv", "bwd:dgrad:output_conv.2", 2.0 * 9 * C * Co * S * S, [=](const RunCtx& rc, cudaStream_t s) {
+                if (dg_mma) {   // same thin-K GEMM as the input conv: dv (fp32 NCHW, C_out channels) x flipped weights -> C channels
+                    const int tiles_img = ((S + IM_TW - 1) / IM_TW) * ((S + IM_TH - 1) / IM_TH);
+                    dim3 grid((tiles_img + IM_TPB - 1) / IM_TPB, rc.B);
+#define RFV_DG_LAUNCH(CI, NT) input_conv_mma_kernel<CI, NT><<<grid, 256, dg_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss)
+                    if (dg_ntc == 8) {
+                        switch (Co) {
+                            case 1: RFV_DG_LAUNCH(1, 8); break;
+                            case 2: RFV_DG_LAUNCH(2, 8); break;
+                            case 3: RFV_DG_LAUNCH(3, 8); break;
+                            default: RFV_DG_LAUNCH(4, 8); break;
+                        }
+                    } else {
+                        switch (Co) {
+                            case 1: RFV_DG_LAUNCH(1, 4); break;
+                            case 2: RFV_DG_LAUNCH(2, 4); break;
+                            case 3: RFV_DG_LAUNCH(3, 4); break;
+                            default: RFV_DG_LAUNCH(4, 4); break;
+                        }
+                    }
+#undef RFV_DG_LAUNCH
+                    return cudaGetLastError();
+                }
                 dim3 grid((S * S + 511) / 512, rc.B);
                 switch (Co) {
                     case 1: input_conv_kernel<1><<<grid, 256, ic_smem, s>>>(dv_buf, nullptr, nullptr, wdg, zero_bias, t0, nullptr, S, S, C, ss); break;
