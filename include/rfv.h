@@ -68,8 +68,9 @@ typedef struct {
                                    second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
 #define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh) instead of a
                                    separate gn_apply pass.  Correct (parity suite passes), but measured SLOWER on B200 at micro-batch
-                                   256: forward 5.05 -> 6.81 ms -- four transform warps cannot keep up with the MMA stream (2 MUFU
-                                   ops per element on a 2.5x halo-redundant box); off by default. */
+                                   256: forward 4.74 -> 5.94 ms (6.81 ms before the one-MUFU SiLU) -- four transform warps would
+                                   have to issue one instruction per clock each to keep up with the MMA stream on a 2x
+                                   halo-redundant box; off by default. */
 #define RFV_FLAG_NO_ATTN_UMMA 8192 /* attention core on the mma.sync kernel even where the tcgen05 one applies (A/B testing) */
 #define RFV_FLAG_GN_BWD_TWO_PASS 16384 /* GroupNorm backward as two streaming passes (reduce, apply) everywhere instead of
                                    the single-pass kernel (A/B testing; the two-pass kernels remain the fallback for pixel counts

@@ -230,6 +230,10 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                         const float4 v = cp[i];
                         sc[2 * i] = v.x; sh[2 * i] = v.y; sc[2 * i + 1] = v.z; sh[2 * i + 1] = v.w;
                     }
+                    if (p.gn_silu) {   // silu(y) = h (1 + tanh h), h = y / 2: one MUFU op per element (see gn_apply_kernel)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { sc[i] *= 0.5f; sh[i] *= 0.5f; }
+                    }
                 }
                 mbar_wait(&afull[st], ph);
                 if (seg0) {
@@ -247,7 +251,13 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const float y = fmaf(f[i], sc[i], sh[i]);
-                                f[i] = p.gn_silu ? silu_f(y) : y;
+                                if (p.gn_silu) {
+                                    float t;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
+                                    f[i] = fmaf(y, t, y);
+                                } else {
+                                    f[i] = y;
+                                }
                             }
                             q = pack8(f);
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
