@@ -81,6 +81,8 @@ typedef struct {
                                    staged pixel followed by a 27-term gather; A/B testing */
 #define RFV_FLAG_INPUT_CONV_FMA 131072 /* input conv on the fp32 FMA pipe (fp32 x and weights) instead of mma.sync with bf16
                                    operands; A/B testing */
+#define RFV_FLAG_TEMB_PER_STEP 262144 /* Euler loops evaluate the time MLP once per step (two single-row launches) instead of
+                                   once per loop for all steps (A/B testing) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict_
     }
 }
 
+// t_i = i * dt in double, rounded once to fp32: what `torch.full((B,), i * dt)` holds in models/base_flow.py:163-166
+__global__ void fill_step_times_kernel(float* __restrict__ t, int n, double dt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = (float)((double)i * dt);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Input conv 3x3, C_in small (<= 4): fp32 NCHW in -> bf16 NHWC out (+ GroupNorm slab statistics).  models/unet.py:165,234
 // Optionally computes the flow-matching interpolation on the fly: x = (1-t) x0 + t x1   (models/base_flow.py:84).
