@@ -66,11 +66,12 @@ typedef struct {
                                   epilogue overlap costs more than the halved weight traffic gains; off by default. */
 #define RFV_FLAG_ONE_STREAM 2048 /* training: run the whole backward pass on one stream (default: weight / bias gradients on a
                                    second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
-#define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh) instead of a
-                                   separate gn_apply pass.  Correct (parity suite passes), but measured SLOWER on B200 at micro-batch
-                                   256: forward 4.74 -> 5.94 ms (6.81 ms before the one-MUFU SiLU) -- four transform warps would
-                                   have to issue one instruction per clock each to keep up with the MMA stream on a 2x
-                                   halo-redundant box; off by default. */
+#define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh: 12 transform
+                                   warps, register budgets re-split with setmaxnreg) in EVERY halo-reuse conv instead of only on
+                                   the 32x32 level.  Parity-green, but slower at 64x64, where the flat 128-position tile needs a
+                                   2.5x halo-redundant box and the transform (issue-bound, ~60 instructions per 8-channel vector)
+                                   outlasts the MMAs: forward 4.72 -> 5.14 ms at micro-batch 256 (4.70 with the default
+                                   selective fusion). */
 #define RFV_FLAG_NO_ATTN_UMMA 8192 /* attention core on the mma.sync kernel even where the tcgen05 one applies (A/B testing) */
 #define RFV_FLAG_GN_BWD_TWO_PASS 16384 /* GroupNorm backward as two streaming passes (reduce, apply) everywhere instead of
                                    the single-pass kernel (A/B testing; the two-pass kernels remain the fallback for pixel counts
@@ -83,6 +84,8 @@ typedef struct {
                                    operands; A/B testing */
 #define RFV_FLAG_TEMB_PER_STEP 262144 /* Euler loops evaluate the time MLP once per step (two single-row launches) instead of
                                    once per loop for all steps (A/B testing) */
+#define RFV_FLAG_NO_FUSE_GN 524288 /* never apply GroupNorm+SiLU inside the consuming conv (by default the sampling plan does so
+                                   on the 32x32 level, where the halo box is only 1.5x the tile and the fused kernel wins) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -26,7 +26,8 @@
 
 namespace rfv {
 
-constexpr int HF_THREADS = 512;
+constexpr int HF_THREADS = 768;      // 4 control warps, 8 epilogue warps, 12 transform warps (register budgets re-split below)
+constexpr int HF_TWARPS = 12;
 
 // scale / shift per (image, channel) of a GroupNorm(8) over a virtual concat of up to two tensors:
 // coef[(n*C + c)*2] = rstd*gamma, coef[..+1] = beta - mean*rstd*gamma
@@ -85,7 +86,7 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapW);
-        for (int s = 0; s < g.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aready[s], 4); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < g.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aready[s], HF_TWARPS); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
         mbar_fence_init();
@@ -100,7 +101,12 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int total_tiles = g.m_tiles * g.n_tiles;
-
+    // 768 threads start with 80 registers each; the epilogue needs ~126.  Warp-group-wide re-split (setmaxnreg):
+    // control 32, transform 64, epilogue 128  ->  128*32 + 384*64 + 256*128 = 61,440 = 768*80: the pool a CTA can re-split is
+    // what it was launched with, not the SM's register file (an `inc` beyond it waits forever).
+    // (each setmaxnreg sits at the top of the branch it governs so that ptxas allocates that branch with its own budget)
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         uint32_t st = 0, ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -210,10 +216,13 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                 if (++ast == (uint32_t)g.a_stages) { ast = 0; aph ^= 1; }
             }
         }
+    }
     } else if (warp >= 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===================== transform: GroupNorm(+SiLU) in place on every segment-0 chunk =====================
-        const int tt = threadIdx.x - 12 * 32;          // 0..127
-        const int j = tt & 7, pl = tt >> 3;            // logical 16-byte vector (8 channels) / position lane (16 lanes)
+        const int tt = threadIdx.x - 12 * 32;          // 0 .. 32*HF_TWARPS-1
+        constexpr int PL = HF_TWARPS * 4;              // position lanes
+        const int j = tt & 7, pl = tt >> 3;            // logical 16-byte vector (8 channels) / position lane
         const int npos = g.rows * g.pitch;
         uint32_t st = 0, ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -238,8 +247,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                 mbar_wait(&afull[st], ph);
                 if (seg0) {
                     const uint32_t base = smem_u32(smem_a + (size_t)st * g.a_stage_bytes);
-                    int rb = pl / g.pitch, cb = pl - rb * g.pitch;   // pl < 16 < pitch: rb = 0
-                    for (int pos = pl; pos < npos; pos += 16) {
+                    int rb = pl / g.pitch, cb = pl - rb * g.pitch;
+                    for (int pos = pl; pos < npos; pos += PL) {
                         const int row = rbox + rb;
                         if (cb >= 1 && row >= 0 && row < g.H) {       // inside the image: padding positions stay zero
                             const uint32_t a = base + (uint32_t)pos * 128;
@@ -262,8 +271,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                             q = pack8(f);
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
                         }
-                        cb += 16;
-                        if (cb >= g.pitch) { cb -= g.pitch; ++rb; }
+                        cb += PL;
+                        while (cb >= g.pitch) { cb -= g.pitch; ++rb; }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the UMMA reads
                 }
@@ -272,7 +281,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                 if (++st == (uint32_t)g.a_stages) { st = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         const int q = warp & 3, grp = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         uint32_t it = grp;

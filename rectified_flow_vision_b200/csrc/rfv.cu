@@ -144,7 +144,8 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false, use_fuse = false;
+    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false;
+    int fuse_mode = 1;   // GroupNorm+SiLU inside the consuming conv: 0 never, 1 where measured faster, 2 wherever the kernel applies
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
@@ -386,7 +387,9 @@ struct rfv_engine {
     struct FuseReq { const float* coef; int C; int silu; ActP second; };   // GroupNorm applied to segment 0 inside the conv
     // can this conv take its GroupNorm(+SiLU) inside the kernel?  (halo-reuse geometry, sampling engines only)
     bool can_fuse_gn(int C0, int Cout, int H, int W) const {
-        return use_fuse && !train && use_umma && use_halo && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
+        // fuse_mode 1 (default): only where the halo box is <= 1.5x the tile (32-pixel rows: four rows per tile); 2: everywhere
+        const bool here = fuse_mode == 2 || (fuse_mode == 1 && W == 32);
+        return here && !train && use_umma && use_halo && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
     }
     int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats,
                 ActP acc_of = nullptr, int acc_k = 0, const FuseReq* fr = nullptr) {
@@ -1613,7 +1616,11 @@ int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
         prof_events.push_back({a, b});
     }
     // Euler loops with a precomputed projection table skip the time-MLP ops; the table fill runs only them
+    // RFV_ONLY_KIND=<kernel class> (diagnosis only, tools/power_by_kind.py): launch just that class, on whatever the buffers
+    // hold -- the results are meaningless, the point is the board power / clock that class draws when run back to back
+    static const char* only_kind = getenv("RFV_ONLY_KIND");
     auto skipped = [&](const Op& op) {
+        if (only_kind && *only_kind && op.kind != only_kind) return true;
         const bool is_temb = op.kind == "temb";
         return rc.temb_only ? !is_temb : (is_temb && rc.temb_row >= 0);
     };
@@ -1761,7 +1768,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
     e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
-    e->use_fuse = (cfg->flags & RFV_FLAG_FUSE_GN) != 0;
+    e->fuse_mode = (cfg->flags & RFV_FLAG_FUSE_GN) ? 2 : ((cfg->flags & RFV_FLAG_NO_FUSE_GN) ? 0 : 1);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
     if (e->train) e->keep_acts = true;  // the backward pass reads every forward activation
     {

@@ -103,8 +103,9 @@ def test_two_lane_sampling_matches_single_lane(monkeypatch):
     assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
 
 
-@pytest.mark.parametrize("flag,name", [(128, "dual M tiles"), (4096, "fused GroupNorm"), (64, "no tap pairing"), (8, "no halo reuse"),
-                                       (512, "cluster-2 weight multicast"), (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"), (131072, "fp32-FMA input conv")])
+@pytest.mark.parametrize("flag,name", [(128, "dual M tiles"), (4096, "GroupNorm fused into every halo conv"), (64, "no tap pairing"), (8, "no halo reuse"),
+                                       (512, "cluster-2 weight multicast"), (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"), (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"),
+                                       (524288, "no GroupNorm fusion")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
     """The A/B kernels kept behind RFV_FLAG_* (include/rfv.h) compute the same velocity as the default plan."""
     from rectified_flow_vision_b200 import engine as E
