@@ -389,9 +389,10 @@ def run_ours(args):
             del peng
             ksplit = {}
             for ln in rep.strip().splitlines():
-                key, ms_tot, n, fl_img = ln.split("\t")
+                key, ms_tot, n, fl_img, by_img = ln.split("\t")
                 kind = key.split(" ", 1)[0] + ("/bwd" if " bwd:" in key else "")
-                k = ksplit.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0})
+                k = ksplit.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0, "mbyte_per_image": 0.0})
+                k["mbyte_per_image"] += float(by_img) / 1e6
                 k["ms"] += float(ms_tot)
                 k["launches"] += int(n)
                 k["gflop_per_image"] += float(fl_img) / 1e9
@@ -405,9 +406,11 @@ def run_ours(args):
                                      "frac_of_burst": ach / pk_["burst"], "peak_source": pk_["source"], "traffic": None,
                                      "flops_per_step": w["gflop_per_image"] * 1e9 * tb, "ms_per_step": w["ms"]}
             if "gn_bwd/bwd" in ksplit:
-                gb = GN_ELEMS_PER_IMAGE * 10.0 * tb   # pass 1 reads 4 B, pass 2 reads 4 B + writes 2 B per element (addends extra)
+                # algorithmic bytes of the launches that ran (engine profile report): single-pass sites 6 B per element (x, dy in;
+                # dx out), two-pass sites 4 + 6 B; addends extra
+                gb = ksplit["gn_bwd/bwd"]["mbyte_per_image"] * 1e6 * tb
                 ach = gb / (ksplit["gn_bwd/bwd"]["ms"] / 1e3) / 1e9
-                train["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_bwd_kernel<false/true> (GroupNorm+SiLU+dropout backward, 60 launches of one step)",
+                train["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_bwd_fused_kernel / gn_bwd_kernel<false/true> (GroupNorm+SiLU+dropout backward, %d launches of one step)" % ksplit["gn_bwd/bwd"]["launches"],
                                          "achieved": ach, "peak": pk_["hbm"], "unit": "GB/s", "frac": ach / pk_["hbm"],
                                          "bytes_per_step": gb, "ms_per_step": ksplit["gn_bwd/bwd"]["ms"]}
         del tr, tmodel, teng
@@ -443,9 +446,10 @@ def run_ours(args):
         eng.set_profiling(False)
         kinds = {}
         for ln in rep.strip().splitlines():
-            key, ms_tot, n, fl_img = ln.split("\t")
+            key, ms_tot, n, fl_img, by_img = ln.split("\t")
             kind, label = key.split(" ", 1)
-            k = kinds.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0})
+            k = kinds.setdefault(kind, {"ms": 0.0, "launches": 0, "gflop_per_image": 0.0, "mbyte_per_image": 0.0})
+            k["mbyte_per_image"] += float(by_img) / 1e6
             k["ms"] += float(ms_tot) / 3.0
             k["launches"] += int(n) // 3
             k["gflop_per_image"] += float(fl_img) / 1e9
@@ -475,9 +479,10 @@ def run_ours(args):
                                                       "frac_of_burst": ach_all / pk["burst"]}}
         if "gn_apply" in kinds:
             # second-largest kernel class, HBM-bound: algorithmic bytes = elements x (2 B read + 2 B written)
-            gb = GN_ELEMS_PER_IMAGE * 4.0 * mb
+            # (bytes of the launches that ran, from the engine's profile report: sites fused into their conv launch nothing)
+            gb = kinds["gn_apply"]["mbyte_per_image"] * 1e6 * mb
             ach = gb / (kinds["gn_apply"]["ms"] / 1e3) / 1e9
-            line["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm + SiLU + virtual concat, 30 launches of one forward)",
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm + SiLU + virtual concat, %d launches of one forward)" % kinds["gn_apply"]["launches"],
                                     "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                     "peak_source": pk["source"], "bytes_per_forward": gb, "ms_per_forward": kinds["gn_apply"]["ms"]}
         # ---- sampling throughput, configs[0] (B=64) and configs[2] (B=4096) ----

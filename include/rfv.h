@@ -177,7 +177,9 @@ double rfv_flops_per_image(rfv_handle h);
  * NCHW (names: "input_conv", "enc_blocks.0", "downsamples.0", "mid_block1", "mid_attn", "dec_blocks.3",
  * "upsamples.1", ...).  Returns the element count, or a negative status.  Test hook. */
 int64_t rfv_debug_activation(rfv_handle h, const char* name, float* dev_out, int64_t capacity, void* stream);
-/* Event-timed duration (ms) of each kernel class inside the last call made with profiling enabled. */
+/* Event-timed duration (ms) of each kernel class inside the last call made with profiling enabled.  The report is one line
+ * per launch site: "<kind> <label>\t<total ms>\t<launches>\t<algorithmic FLOPs per image>\t<algorithmic HBM bytes per image>"
+ * (bytes are set for the HBM-bound GroupNorm kernels, 0 elsewhere). */
 int rfv_set_profiling(rfv_handle h, int enabled);
 int rfv_profile_report(rfv_handle h, char* buf, int buf_len);
 

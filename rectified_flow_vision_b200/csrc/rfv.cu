@@ -116,6 +116,7 @@ struct Op {
     std::string label;   // e.g. "conv:enc_blocks.0.conv1"
     std::string kind;    // kernel class for the profile report
     double flops = 0;    // algorithmic FLOPs per image
+    double bytes = 0;    // algorithmic HBM bytes per image (HBM-bound kernels: GroupNorm apply / backward), else 0
     std::function<cudaError_t(const RunCtx&, cudaStream_t)> run;
     int lane = 0;        // backward pass: 0 = main stream, 1 = side stream (weight / bias gradients)
     int sync = 0;        // 1: the side stream first waits for everything enqueued on main; 2: main first waits for side
@@ -355,6 +356,7 @@ struct rfv_engine {
         if (rec == &ops) flops_per_image += flops;
         rec->push_back(std::move(op));
     }
+    void set_last_bytes(double bytes) { rec->back().bytes = bytes; }
 
     int make_map4(CUtensorMap* m, const bf16* base, int C, int Wd, int Hd, int Nd, size_t sW, size_t sH, size_t sN,
                   int bw, int bh, int bn) {
@@ -737,6 +739,7 @@ struct rfv_engine {
                                                                          dt_, rc.seed ^ ((uint32_t)site_id * 0x9E3779B9u), rc.drop_scale);
             return cudaGetLastError();
         });
+        set_last_bytes(4.0 * C * HW);   // 2 B read + 2 B written per element
         return 0;
     }
 
@@ -1047,6 +1050,7 @@ struct rfv_engine {
                 gn_bwd_fused_kernel<<<SL * rc.B, threads, smem, s>>>(q, SL);
                 return cudaGetLastError();
             });
+            set_last_bytes(6.0 * C * st.HW);   // x and dy in, dx out (addends extra)
             return 0;
         }
         push("gn_bwd", "bwd:gn_reduce:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
@@ -1056,6 +1060,7 @@ struct rfv_engine {
             gn_bwd_kernel<false><<<grid, threads, 2 * C * sizeof(float), s>>>(q);
             return cudaGetLastError();
         });
+        set_last_bytes(4.0 * C * st.HW);    // pass 1: x and dy in
         push("gn_bwd", "bwd:gn_apply:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             GnBwdArgs q = a;
             fill(q, rc);
@@ -1063,6 +1068,7 @@ struct rfv_engine {
             gn_bwd_kernel<true><<<grid, threads, q.out_colsum ? C * sizeof(float) : 0, s>>>(q);
             return cudaGetLastError();
         });
+        set_last_bytes(6.0 * C * st.HW);    // pass 2: x and dy in, dx out (addends extra)
         return 0;
     }
 
@@ -2122,13 +2128,14 @@ RFV_EXPORT int rfv_profile_report(rfv_handle h, char* buf, int buf_len) {
     if (!h || !buf || buf_len < 1) return fail(RFV_ERR_INVALID, "bad argument");
     std::string out;
     char line[512];
-    std::map<std::string, double> flops;
-    for (auto& op : h->ops) flops[op.kind + " " + op.label] = op.flops;
+    std::map<std::string, double> flops, bytes;
+    for (auto& op : h->ops) { flops[op.kind + " " + op.label] = op.flops; bytes[op.kind + " " + op.label] = op.bytes; }
     for (auto& blk : h->bwd_blocks)
-        for (auto& op : blk) flops[op.kind + " " + op.label] = op.flops;
-    for (auto& kv : h->prof) {  // "<kind> <label>\t<total ms>\t<launches>\t<algorithmic FLOPs per image>"
-        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\t%.1f\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second,
-                 flops[kv.first]);
+        for (auto& op : blk) { flops[op.kind + " " + op.label] = op.flops; bytes[op.kind + " " + op.label] = op.bytes; }
+    // "<kind> <label>\t<total ms>\t<launches>\t<algorithmic FLOPs per image>\t<algorithmic HBM bytes per image>"
+    for (auto& kv : h->prof) {
+        snprintf(line, sizeof(line), "%s\t%.6f\t%lld\t%.1f\t%.1f\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second,
+                 flops[kv.first], bytes[kv.first]);
         out += line;
     }
     snprintf(buf, buf_len, "%s", out.c_str());

@@ -43,7 +43,7 @@ def main():
     eng.set_profiling(False)
     rows = []
     for ln in rep.strip().splitlines():
-        key, ms, n, fl = ln.split("\t")
+        key, ms, n, fl, _by = ln.split("\t")
         rows.append((key, float(ms) / a.reps, float(fl) * a.mb))
     tot = sum(r[1] for r in rows)
     kinds = {}

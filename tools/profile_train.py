@@ -61,7 +61,7 @@ def main():
     eng.set_profiling(False)
     rows = []
     for ln in rep.strip().splitlines():
-        key, ms, n, f = ln.split("\t")
+        key, ms, n, f, _by = ln.split("\t")
         rows.append((key, float(ms) / a.reps, float(f) * a.mb))
     tot = sum(r[1] for r in rows)
     kinds = {}
