@@ -246,33 +246,49 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                 }
                 mbar_wait(&afull[st], ph);
                 if (seg0) {
+                    // Stage buffers are 1024-byte aligned and the position stride PL is a multiple of 8, so the 128B-swizzle term
+                    // of this thread's 16-byte vector, j ^ (position & 7), is the same for every position it visits: the address
+                    // just advances by PL rows.  Two positions per iteration give the scheduler two independent dependency
+                    // chains (load -> unpack -> FMA -> MUFU -> FMA -> pack -> store); the loop is issue-bound.
                     const uint32_t base = smem_u32(smem_a + (size_t)st * g.a_stage_bytes);
+                    const int row_lo = max(0, -rbox), row_hi = min(g.rows, g.H - rbox);   // box rows inside the image
+                    uint32_t addr = base + (uint32_t)pl * 128 + (uint32_t)((j ^ (pl & 7)) << 4);
                     int rb = pl / g.pitch, cb = pl - rb * g.pitch;
-                    for (int pos = pl; pos < npos; pos += PL) {
-                        const int row = rbox + rb;
-                        if (cb >= 1 && row >= 0 && row < g.H) {       // inside the image: padding positions stay zero
-                            const uint32_t a = base + (uint32_t)pos * 128;
-                            const uint32_t addr = a + (uint32_t)((j ^ ((a >> 7) & 7)) << 4);
-                            uint4 q;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-                            float f[8];
-                            unpack8(q, f);
+                    auto advance = [&](int& r_, int& c_) {
+                        c_ += PL;
+                        while (c_ >= g.pitch) { c_ -= g.pitch; ++r_; }
+                    };
+                    auto xform = [&](uint4& q) {
+                        float f[8];
+                        unpack8(q, f);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float y = fmaf(f[i], sc[i], sh[i]);
-                                if (p.gn_silu) {
-                                    float t;
-                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
-                                    f[i] = fmaf(y, t, y);
-                                } else {
-                                    f[i] = y;
-                                }
+                        for (int i = 0; i < 8; ++i) {
+                            const float y = fmaf(f[i], sc[i], sh[i]);
+                            if (p.gn_silu) {
+                                float t;
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
+                                f[i] = fmaf(y, t, y);
+                            } else {
+                                f[i] = y;
                             }
-                            q = pack8(f);
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
                         }
-                        cb += PL;
-                        while (cb >= g.pitch) { cb -= g.pitch; ++rb; }
+                        q = pack8(f);
+                    };
+                    for (int pos = pl; pos < npos; pos += 2 * PL, addr += 2 * PL * 128) {
+                        int rb1 = rb, cb1 = cb;
+                        advance(rb1, cb1);
+                        // padding positions (column 0, rows outside the image) stay zero
+                        const bool v0 = cb >= 1 && rb >= row_lo && rb < row_hi;
+                        const bool v1 = pos + PL < npos && cb1 >= 1 && rb1 >= row_lo && rb1 < row_hi;
+                        uint4 q0, q1;
+                        if (v0) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(addr));
+                        if (v1) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(addr + PL * 128));
+                        if (v0) xform(q0);
+                        if (v1) xform(q1);
+                        if (v0) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q0.x), "r"(q0.y), "r"(q0.z), "r"(q0.w) : "memory");
+                        if (v1) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + PL * 128), "r"(q1.x), "r"(q1.y), "r"(q1.z), "r"(q1.w) : "memory");
+                        rb = rb1; cb = cb1;
+                        advance(rb, cb);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the UMMA reads
                 }
