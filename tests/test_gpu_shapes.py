@@ -1,8 +1,10 @@
 """GPU parity on shapes the golden cases do not cover: images narrower than one output-conv / input-conv tile, grayscale and
 4-channel images, two-level networks.  Every masked edge of the thin-conv tiles, the GroupNorm slice selection of the
 single-pass backward (tiny HW) and the C_out = 4 fallback of the output conv runs here, compared with the CPU oracle
-(oracle/unet_oracle.py, oracle/train_oracle.py) on seeded inputs; plus guard bands around caller buffers (compute-sanitizer is
-not available on the GPU pool, so out-of-bounds writes at the API boundary are looked for with sentinels).
+(oracle/unet_oracle.py, oracle/train_oracle.py) on seeded inputs AND with outputs of the reference itself on the same seeds
+(tests/golden/shapes_*.npz from oracle/make_golden_shapes.py; tests/test_oracle_shapes_golden.py pins the oracles to them); plus
+guard bands around caller buffers (compute-sanitizer is not available on the GPU pool, so out-of-bounds writes at the API
+boundary are looked for with sentinels).
 
 Tolerances as tests/test_gpu_parity.py / tests/test_gpu_train.py: velocity rel-L2 <= 3e-2 against the fp32 oracle, <= 2e-2
 against the bf16-policy oracle; per-tensor gradient rel-L2 <= 5e-2."""
@@ -15,7 +17,7 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 SHAPES = {
-    # name: (image_size, in_channels, model_channels, channel_mult, num_res_blocks)
+    # name: (image_size, in_channels, model_channels, channel_mult, num_res_blocks)   -- as oracle/make_golden_shapes.py
     "16px_two_levels": (16, 3, 64, [1, 2], 1),         # W = 16 < 32-pixel tile width; lowest level 8x8 = 64 tokens, head dim 32
     "gray_32px": (32, 1, 64, [1, 2, 4], 1),            # C_in = C_out = 1 (K = 9 -> 16 in the input conv, 9 Z columns)
     "four_channel_32px": (32, 4, 64, [1, 2, 4], 1),    # C_in = 4 (K = 36 -> 48), C_out = 4 -> tap-shifted output conv
@@ -26,7 +28,7 @@ def _build(name):
     import rectified_flow_vision_b200 as pkg
     from oracle.unet_oracle import UNetSpec
     S, cin, mc, mult, nres = SHAPES[name]
-    torch.manual_seed(1234)
+    torch.manual_seed(1234)                            # seed / input seed / batch of the golden files
     m = pkg.RectifiedFlowModel(image_size=S, in_channels=cin, model_channels=mc, channel_mult=mult, num_res_blocks=nres,
                                device="cpu")
     m.device = "cuda:0"
@@ -52,6 +54,13 @@ def test_velocity_vs_oracle(name):
     pol = O.unet_forward(P, x.numpy(), t.numpy(), spec, policy=O.BF16_POLICY)
     assert util.rel_l2(v, ref) <= 3e-2, (name, util.rel_l2(v, ref))
     assert util.rel_l2(v, pol) <= 2e-2, (name, util.rel_l2(v, pol))
+    g = np.load(f"{util.GOLD}/shapes_{name}.npz")      # the reference's own forward and 3-step Euler on the same seeds
+    assert np.array_equal(g["x"], x.numpy()) and np.array_equal(g["t"], t.numpy())
+    assert util.rel_l2(v, g["v"]) <= 3e-2, (name, util.rel_l2(v, g["v"]))
+    with torch.no_grad():
+        s3 = m.sample(x.cuda(), num_steps=3).cpu().numpy()
+    assert util.rel_l2(s3, g["sample_3"]) <= 1e-2, (name, util.rel_l2(s3, g["sample_3"]))
+    assert util.psnr(s3, g["sample_3"]) >= 45.0, name
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
@@ -129,3 +138,15 @@ def test_training_gradients_vs_oracle(name):
         g = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape)
         assert np.isfinite(g).all(), k
         assert util.rel_l2(g, gr.numpy()) <= 5e-2, (name, k, util.rel_l2(g, gr.numpy()))
+    # ... and against the reference's own loss.backward() on the same seeds
+    gold = np.load(f"{util.GOLD}/shapes_{name}.npz")
+    assert np.array_equal(gold["x"], x0.numpy()) and np.array_equal(gold["x1"], x1.numpy())
+    assert abs(loss - float(gold["loss"])) <= 5e-3 * float(gold["loss"])
+    ref_norm = gold["grad_norm_per_tensor"]
+    for k, rn in zip([str(n) for n in gold["names"]], ref_norm):
+        if rn < 1e-3 * ref_norm.max():
+            continue
+        full = eng.get_grad(k, grads[k].numel()).cpu().numpy().reshape(-1)
+        assert abs(float(np.linalg.norm(full.astype(np.float64))) - rn) <= 5e-2 * rn, (name, k)
+        if gold["grad_sampled/" + k].size >= 64:          # every 241st element: only meaningful on the large tensors
+            assert util.rel_l2(full[::241], gold["grad_sampled/" + k]) <= 5e-2, (name, k, util.rel_l2(full[::241], gold["grad_sampled/" + k]))
