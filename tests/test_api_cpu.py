@@ -115,3 +115,20 @@ def test_benchmark_csv_schema_matches_reference(tmp_path):
     lines = out.read_text().strip().splitlines()
     assert lines[0] == "num_steps,base_time_ms,rect_time_ms,base_img_per_sec,rect_img_per_sec,speedup"
     assert len(lines) == 3 and lines[1].startswith("1,") and lines[1].endswith(",1.0")
+
+
+def test_engine_flags_are_distinct_bits():
+    """include/rfv.h: every RFV_FLAG_* is its own bit, clear of the cluster-size field (bits 8-10) -- two switches sharing a bit
+    would silently change which kernel an A/B test measures."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rfv.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(RFV_FLAG_\w+)\s+(\d+)", hdr)}
+    assert len(flags) >= 15
+    seen = 0
+    for name, v in flags.items():
+        assert v > 0 and v & (v - 1) == 0, (name, v)
+        assert not (v & seen), name
+        assert not (v & (7 << 8)), name
+        seen |= v
+    from rectified_flow_vision_b200 import engine as E
+    assert E.FLAG_TRAIN == flags["RFV_FLAG_TRAIN"]
