@@ -64,6 +64,9 @@ typedef struct {
 #define RFV_FLAG_DUAL      128 /* 256-output-channel convs: share each weight slice between two M tiles (conv_umma_dual_kernel).
                                   Measured on B200 at micro-batch 256: 1.49 ms vs 1.43 ms for the 18 launches -- the lost
                                   epilogue overlap costs more than the halved weight traffic gains; off by default. */
+/* bits 8-10 (values 256 / 512 / 1024) are not switches but a field: (flags >> 8) & 7 = CTAs per cluster for TMA weight
+ * multicast in the per-tap tcgen05 conv kernel (2 or 4; measured slower than 1 on B200: forward 5.11 / 5.29 / 5.36 ms at
+ * cluster 1 / 2 / 4, micro-batch 256). */
 #define RFV_FLAG_ONE_STREAM 2048 /* training: run the whole backward pass on one stream (default: weight / bias gradients on a
                                    second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
 #define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh: 12 transform
