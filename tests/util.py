@@ -67,3 +67,33 @@ def max_rel(a, b):
 def psnr(a, b, peak=2.0):
     mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
     return 10 * np.log10(peak * peak / max(mse, 1e-30))
+
+
+def weights_manifest():
+    with open(os.path.join(GOLD, "weights_manifest.json")) as f:
+        return json.load(f)
+
+
+def perturbed_model(case, device="cpu", cls=None):
+    """The package model of a `pert_*` golden case: seeded constructor weights rewritten by oracle/perturb.py -- the same
+    function the reference-side generator (oracle/make_golden_weights.py) applied before `load_state_dict`.  Both sha256
+    fingerprints in the manifest are re-checked, so the weights are bit-identical to the reference's."""
+    import rectified_flow_vision_b200 as pkg
+    from oracle.perturb import perturb_state_dict
+    cls = cls or pkg.BaseFlowModel
+    man = weights_manifest()
+    c = man["cases"][case]
+    torch.manual_seed(c["seed"])
+    m = cls(device="cpu", **c["kwargs"])
+    assert state_sha(m.state_dict()) == c["init_sha256"], "seeded initialisation differs from the reference's"
+    m.load_state_dict(perturb_state_dict(m.state_dict(), man["perturb_seed"]))
+    assert state_sha(m.state_dict()) == c["state_sha256"], "perturbed weights differ from the reference's"
+    if device != "cpu":
+        m.device = device
+        m.to(device)
+    return m
+
+
+def arch_of(kwargs):
+    return dict(model_channels=kwargs.get("model_channels", 64), channel_mult=tuple(kwargs.get("channel_mult", [1, 2, 4])),
+                num_res_blocks=kwargs.get("num_res_blocks", 2))
