@@ -207,9 +207,18 @@ def test_natively_trained_weights(kw, size, steps_train):
     eng.zero_grad()
     loss = float(eng.train_accumulate(xt.cuda(), x1t.cuda(), t.cuda(), dropout_p=0.0, seed=1).item())
     assert abs(loss - loss_ref) <= TOL_LOSS * loss_ref
+    # Per-tensor bound: 5e-2 rel-L2 where the tensor carries a significant share of the gradient (>= 1e-2 of the largest
+    # tensor norm); tensors below that are sums that cancel almost completely, so the bf16 rounding of the activation
+    # gradients shows up relative to the un-cancelled magnitude -- they are held to the same ABSOLUTE error a significant
+    # tensor would be allowed (5e-2 * 1e-2 * gmax).  The whole gradient's direction is checked on top.
     gmax = max(float(gr.norm()) for gr in grads.values())
+    dot = nn_ = nr_ = 0.0
     for k, gr in grads.items():
-        if float(gr.norm()) < 1e-3 * gmax:
-            continue
-        got = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape)
-        assert util.rel_l2(got, gr.numpy()) <= TOL_GRAD_L2, (k, util.rel_l2(got, gr.numpy()))
+        got = eng.get_grad(k, gr.numel()).cpu().numpy().reshape(gr.shape).astype(np.float64)
+        ref = gr.numpy().astype(np.float64)
+        err = float(np.sqrt(((got - ref) ** 2).sum()))
+        bound = TOL_GRAD_L2 * max(float(gr.norm()), 1e-2 * gmax)
+        assert err <= bound, (k, err / max(float(gr.norm()), 1e-30), float(gr.norm()) / gmax)
+        dot += float((got * ref).sum()); nn_ += float((got ** 2).sum()); nr_ += float((ref ** 2).sum())
+    cos = dot / np.sqrt(nn_ * nr_)
+    assert cos >= 0.9995 and abs(np.sqrt(nn_ / nr_) - 1) <= TOL_GNORM, (cos, np.sqrt(nn_ / nr_))
