@@ -56,9 +56,8 @@ typedef struct {
 #define RFV_FLAG_NO_GRAPH  2   /* launch kernels directly instead of replaying a captured CUDA graph */
 #define RFV_FLAG_KEEP_ACTS 4   /* never recycle activation buffers, so rfv_debug_activation can read any layer */
 #define RFV_FLAG_NO_HALO   8   /* do not use the halo-reuse tcgen05 kernel (A/B testing against the per-tap kernel) */
-#define RFV_FLAG_BASEOFF   16  /* halo kernel: also set the UMMA descriptor base-offset field to (addr>>7)&7.  Measured on
-                                  B200: WRONG results -- the 128B swizzle is applied on absolute smem address bits, so
-                                  shifted (128-byte aligned) start addresses need base offset 0.  Kept as an experiment. */
+#define RFV_FLAG_NO_DOUBLE_TILE 16 /* halo-reuse convs with streamed weights: 128-position tiles instead of 256-position double
+                                  tiles (two accumulators per weight block); A/B testing */
 
 #define RFV_FLAG_NO_PAIR   64  /* 64-output-channel 3x3 convs: one tap per MMA (N = 64) instead of two (N = 128); A/B testing */
 #define RFV_FLAG_DUAL      128 /* 256-output-channel convs: share each weight slice between two M tiles (conv_umma_dual_kernel).

@@ -133,6 +133,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* map, uint64_
         : "memory");
 }
 
+// Tiled TMA store shared -> global (bulk async-group completion).  Elements of the box beyond the tensor's upper bounds are
+// not written; a NEGATIVE start coordinate, which loads accept, raises "illegal instruction" on a store (measured on B200,
+// tools/micro/tma_store_test.cu).
+__device__ __forceinline__ void tma_store_3d(const void* map, const void* smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // writes complete
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): `bytes` multiple of 16, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -63,7 +63,8 @@ template <int BN>
 __global__ void __launch_bounds__(HF_THREADS, 1)
 conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA0b,
                        const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
-                       const __grid_constant__ CUtensorMap mapW, const ConvParams p, const HaloGeom g) {
+                       const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO32, const __grid_constant__ CUtensorMap mapO31, const ConvParams p,
+                       const HaloGeom g) {
     constexpr int B_BYTES = BN * 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -72,7 +73,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     const int nkb0 = 9 * g.cch0, nkb = nkb0 + g.cch1a + g.cch1b;
     const int nch = g.cch0 + g.cch1a + g.cch1b;
     const int b_slots = g.resident_b ? nkb : g.b_stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)b_slots * B_BYTES);
+    uint8_t* smem_o = smem_b + (size_t)b_slots * B_BYTES;   // epilogue boxes: 8 warps x 4 KB (conv_epilogue_halo)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 8 * HALO_STAGE_BYTES);
     uint64_t* afull = bars;                      // TMA -> transform
     uint64_t* aready = afull + g.a_stages;       // transform -> MMA
     uint64_t* aempty = aready + g.a_stages;      // MMA -> TMA
@@ -86,6 +88,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapO32);
+        tma_prefetch_desc(&mapO31);
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aready[s], HF_TWARPS); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < g.b_stages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
@@ -94,7 +98,8 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
     if (threadIdx.x < 32)
         for (int s = 0; s < g.a_stages; ++s)
             reinterpret_cast<uint32_t*>(smem_a + (size_t)s * g.a_stage_bytes + g.a_box_bytes)[threadIdx.x] = 0u;
-    if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
+    const int tile_pos = 128 * g.sub;   // double tiles: see conv_halo.cuh
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * g.sub * BN);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -112,7 +117,7 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / g.n_tiles;
             const int n = mt / g.tiles_per_img, ti = mt - n * g.tiles_per_img;
-            const int rbox = (ti * 128) / g.pitch - 1;
+            const int rbox = (ti * tile_pos) / g.pitch - 1;
             for (int ch = 0; ch < nch; ++ch) {
                 mbar_wait(&aempty[st], ph ^ 1);
                 if (elect_one()) {
@@ -160,12 +165,13 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / g.n_tiles;
             const int ti = mt % g.tiles_per_img;
-            const int q0 = ti * 128;
+            const int q0 = ti * tile_pos;
             const int idx0 = q0 - (q0 / g.pitch - 1) * g.pitch;
+            const int nsub = (g.sub == 2 && q0 + 128 < g.H * g.pitch) ? 2 : 1;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(&tempty[as], aphase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
+            const uint32_t d_tmem = tmem_base + as * (g.sub * BN);
             for (int ch = 0; ch < nch; ++ch) {
                 mbar_wait(&aready[ast], aph);       // the chunk has been normalised in place
                 tc_fence_after();
@@ -179,14 +185,19 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                                 const int shift = (tap / 3 - 1) * g.pitch + (tap % 3 - 1);
                                 const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(shift * 128));
                                 const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)(tap * g.cch0 + ch) * B_BYTES));
+                                for (int sb = 0; sb < nsub; ++sb) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (ch | tap | j) != 0);
+                                    for (int j = 0; j < 4; ++j)
+                                        umma_bf16(d_tmem + sb * BN, adesc + sb * 1024 + 2 * j, bdesc + 2 * j, idesc, (ch | tap | j) != 0);
+                                }
                             }
                         } else {
                             const uint64_t adesc = umma_desc_sw128(abase);
                             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)(nkb0 + ch - g.cch0) * B_BYTES));
+                            for (int sb = 0; sb < nsub; ++sb) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, 1u);
+                                for (int j = 0; j < 4; ++j) umma_bf16(d_tmem + sb * BN, adesc + sb * 1024 + 2 * j, bdesc + 2 * j, idesc, 1u);
+                            }
                         }
                         umma_commit(&aempty[ast]);
                         if (ch == nch - 1) umma_commit(&tfull[as]);
@@ -201,8 +212,11 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
                         if (elect_one()) {
                             const uint64_t adesc = umma_desc_sw128(abase + (uint32_t)(shift * 128));
                             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)bst * B_BYTES));
+                            for (int sb = 0; sb < nsub; ++sb) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (ch | tap | j) != 0);
+                                for (int j = 0; j < 4; ++j)
+                                    umma_bf16(d_tmem + sb * BN, adesc + sb * 1024 + 2 * j, bdesc + 2 * j, idesc, (ch | tap | j) != 0);
+                            }
                             umma_commit(&bempty[bst]);
                             if (tap == ntaps - 1) {
                                 umma_commit(&aempty[ast]);
@@ -228,7 +242,7 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / g.n_tiles;
             const int n = mt / g.tiles_per_img, ti = mt - n * g.tiles_per_img;
-            const int rbox = (ti * 128) / g.pitch - 1;
+            const int rbox = (ti * tile_pos) / g.pitch - 1;
             for (int ch = 0; ch < nch; ++ch) {
                 float sc[8], sh[8];
                 const bool seg0 = ch < g.cch0;
@@ -305,18 +319,22 @@ conv_halo_fused_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_c
         for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
             const int mt = tile / g.n_tiles, nt = tile - mt * g.n_tiles;
             const int n = mt / g.tiles_per_img, ti = mt - n * g.tiles_per_img;
-            const int pos = ti * 128 + r;
-            const int rr = pos / g.pitch, cc = pos - rr * g.pitch;
-            const bool n_ok = n < p.B;
-            const bool valid = n_ok && cc >= 1 && rr < g.H;
-            const size_t pix = ((size_t)n * g.H + rr) * g.W + (cc - 1);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
-            conv_epilogue_tile<BN>(p, taddr, n, n_ok, valid, pix, nt, lane, &tfull[grp], (it >> 1) & 1, &tempty[grp]);
+            const int nsub = (g.sub == 2 && ti * tile_pos + 128 < g.H * g.pitch) ? 2 : 1;
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int pos = ti * tile_pos + sb * 128 + r;
+                const int rr = pos / g.pitch, cc = pos - rr * g.pitch;
+                const bool valid = cc >= 1 && rr < g.H;     // (m_tiles = B * tiles_per_img: every tile lies inside the batch)
+                const size_t pix = ((size_t)n * g.H + rr) * g.W + (cc - 1);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * (g.sub * BN) + sb * BN;
+                conv_epilogue_halo<BN>(p, &mapO32, &mapO31, smem_o + (warp - 4) * HALO_STAGE_BYTES, taddr, n, valid, pix, nt, lane, pos - lane,
+                                       g.pitch, &tfull[grp], (it >> 1) & 1, &tempty[grp], sb == nsub - 1);
+            }
         }
+        if (lane == 0) bulk_wait_all0();   // this lane's TMA stores must have left shared memory (and landed) before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * g.sub * BN);
 }
 
 }  // namespace rfv

@@ -370,6 +370,17 @@ struct rfv_engine {
         if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
         return 0;
     }
+    // output of a halo-reuse conv as {C, H*W pixels, N}: box = 64 channels x `box_pix` consecutive pixels (conv_epilogue_halo)
+    int make_map_pix(CUtensorMap* m, const bf16* base, int C, int HW, int Nd, int box_pix) {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)Nd};
+        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)HW * C * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)box_pix, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+        return 0;
+    }
     int make_map2(CUtensorMap* m, const bf16* base, int K, int rows, int box_rows) {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
         cuuint64_t strides[1] = {(cuuint64_t)K * 2};
@@ -393,6 +404,46 @@ struct rfv_engine {
         const bool here = fuse_mode == 2 || (fuse_mode == 1 && W == 32);
         return here && !train && use_umma && use_halo && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
     }
+    // Geometry and shared-memory plan of a halo-reuse conv (conv_halo.cuh / conv_halo_fused.cuh).  Layers whose weights do
+    // not fit shared memory run DOUBLE tiles (256 positions: every streamed weight block feeds two accumulators).
+    int plan_halo(HaloGeom* gp, int* BNp, size_t* smem, const ConvLayer* L, int W, int H, int bo_mode) {
+        HaloGeom& g = *gp;
+        g.W = W; g.H = H; g.pitch = W + 1;
+        g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+        const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
+        *BNp = BN;
+        g.n_tiles = L->Cout / BN;
+        g.base_offset_mode = bo_mode;
+        const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
+        const int avail = 227 * 1024 - 2048 - 512 - 8 * HALO_STAGE_BYTES;   // 8 epilogue warps x one 4 KB TMA-store box
+        const int bbytes = BN * 128;
+        auto shape = [&](int sub) {
+            g.sub = sub;
+            g.rows = (g.pitch - 1 + 128 * sub - 1) / g.pitch + 1 + 2;
+            g.tiles_per_img = (g.H * g.pitch + 128 * sub - 1) / (128 * sub);
+            g.a_box_bytes = g.rows * g.pitch * 128;
+            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
+        };
+        shape(1);
+        g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
+        if (g.resident_b && (avail - nkb * bbytes) / g.a_stage_bytes < 2) g.resident_b = 0;   // wide images: the boxes need the room
+        int bregion;
+        if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
+        else {
+            g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+            bregion = g.b_stages * bbytes;
+            if (BN <= 128 && !(cfg.flags & RFV_FLAG_NO_DOUBLE_TILE)) {
+                shape(2);
+                if ((avail - 3 * bbytes) / g.a_stage_bytes < 2) shape(1);   // very wide rows: two double-tile boxes do not fit
+            }
+            while (g.b_stages > 3 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
+        }
+        g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
+        if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
+        *smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 8 * HALO_STAGE_BYTES + 512;
+        return 0;
+    }
+
     int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats,
                 ActP acc_of = nullptr, int acc_k = 0, const FuseReq* fr = nullptr) {
         const std::string pre = rec == &ops ? "conv:" : "bwd:dgrad:";
@@ -425,32 +476,12 @@ struct rfv_engine {
         if (fr) {
             // halo-reuse kernel with GroupNorm(+SiLU) applied to the segment-0 chunks in shared memory (conv_halo_fused.cuh)
             if (!halo_ok) return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
-            struct FBundle { CUtensorMap a0, a0b, a1, a2, w; HaloGeom g; int BN; size_t smem; };
+            struct FBundle { CUtensorMap a0, a0b, a1, a2, w, o32, o31; HaloGeom g; int BN; size_t smem; };
             auto bd = std::make_shared<FBundle>();
             HaloGeom& g = bd->g;
-            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
-            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
-            g.tiles_per_img = (g.H * g.pitch + 127) / 128;
-            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
             g.cch0a = in0->C / 64;
-            const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
-            bd->BN = BN;
-            g.n_tiles = L->Cout / BN;
-            g.a_box_bytes = g.rows * g.pitch * 128;
-            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
-            g.base_offset_mode = 0;
-            const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
-            const int avail = 227 * 1024 - 2048 - 512;
-            const int bbytes = BN * 128;
-            g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
-            int bregion;
-            if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
-            else { g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8); bregion = g.b_stages * bbytes; }
-            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) { g.resident_b = 0; g.b_stages = 8; bregion = g.b_stages * bbytes; }
-            while (!g.resident_b && g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
-            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
-            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
-            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 512;
+            RFV_TRY(plan_halo(&g, &bd->BN, &bd->smem, L, out->W, out->H, 0));
+            const int BN = bd->BN;
             auto amap = [&](CUtensorMap* m, const ActP& t) {
                 return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
             };
@@ -460,6 +491,8 @@ struct rfv_engine {
             if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
             if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
             RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            RFV_TRY(make_map_pix(&bd->o32, out->p, out->C, out->H * out->W, cap, 32));
+            RFV_TRY(make_map_pix(&bd->o31, out->p, out->C, out->H * out->W, cap, 31));
             p.gn_coef = fr->coef; p.gn_C = fr->C; p.gn_silu = fr->silu;
             const int sms = num_sms, sumC_ = sumC;
             push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
@@ -471,9 +504,9 @@ struct rfv_engine {
                 g.m_tiles = rc.B * g.tiles_per_img;
                 const int grid = std::min(g.m_tiles * g.n_tiles, sms);
                 switch (bd->BN) {
-                    case 256: conv_halo_fused_kernel<256><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g); break;
-                    case 128: conv_halo_fused_kernel<128><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g); break;
-                    default: conv_halo_fused_kernel<64><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, q, g);
+                    case 256: conv_halo_fused_kernel<256><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
+                    case 128: conv_halo_fused_kernel<128><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
+                    default: conv_halo_fused_kernel<64><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g);
                 }
                 return cudaGetLastError();
             });
@@ -526,35 +559,11 @@ struct rfv_engine {
                 return cudaGetLastError();
             });
         } else if (halo_ok) {
-            struct HBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; int BN; size_t smem; };
+            struct HBundle { CUtensorMap a0, a1, a2, w, o32, o31; HaloGeom g; int BN; size_t smem; };
             auto bd = std::make_shared<HBundle>();
             HaloGeom& g = bd->g;
-            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
-            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
-            g.tiles_per_img = (g.H * g.pitch + 127) / 128;
-            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
-            const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
-            bd->BN = BN;
-            g.n_tiles = L->Cout / BN;
-            g.a_box_bytes = g.rows * g.pitch * 128;
-            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
-            g.base_offset_mode = base_offset_mode;
-            const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
-            const int avail = 227 * 1024 - 2048 - 512;
-            const int bbytes = BN * 128;
-            g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
-            int bregion;
-            if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
-            else { g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8); bregion = g.b_stages * bbytes; }
-            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) {  // wide images: the halo boxes need the room
-                g.resident_b = 0;
-                g.b_stages = 8;
-                bregion = g.b_stages * bbytes;
-            }
-            while (!g.resident_b && g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
-            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
-            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
-            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 512;
+            RFV_TRY(plan_halo(&g, &bd->BN, &bd->smem, L, out->W, out->H, base_offset_mode));
+            const int BN = bd->BN;
             auto amap = [&](CUtensorMap* m, const ActP& t) {
                 return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
             };
@@ -563,6 +572,8 @@ struct rfv_engine {
             if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
             if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
             RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
+            RFV_TRY(make_map_pix(&bd->o32, out->p, out->C, out->H * out->W, cap, 32));
+            RFV_TRY(make_map_pix(&bd->o31, out->p, out->C, out->H * out->W, cap, 31));
             const int sms = num_sms, sumC_ = sumC;
             push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
                 ConvParams q = p;
@@ -574,9 +585,9 @@ struct rfv_engine {
                 g.m_tiles = rc.B * g.tiles_per_img;
                 const int grid = std::min(g.m_tiles * g.n_tiles, sms);
                 switch (bd->BN) {
-                    case 256: conv_halo_kernel<256><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g); break;
-                    case 128: conv_halo_kernel<128><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g); break;
-                    default: conv_halo_kernel<64><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                    case 256: conv_halo_kernel<256><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
+                    case 128: conv_halo_kernel<128><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
+                    default: conv_halo_kernel<64><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g);
                 }
                 return cudaGetLastError();
             });
@@ -1782,7 +1793,6 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
         if (c == 1 || c == 2 || c == 4) e->cluster = c;
         else if (c != 0) return fail(RFV_ERR_INVALID, "cluster size override must be 1, 2 or 4");
     }
-    e->base_offset_mode = (cfg->flags & RFV_FLAG_BASEOFF) ? 1 : 0;
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
     {

@@ -103,7 +103,7 @@ def test_two_lane_sampling_matches_single_lane(monkeypatch):
     assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
 
 
-@pytest.mark.parametrize("flag,name", [(128, "dual M tiles"), (4096, "GroupNorm fused into every halo conv"), (64, "no tap pairing"), (8, "no halo reuse"),
+@pytest.mark.parametrize("flag,name", [(16, "128-position tiles (no double tiles)"), (128, "dual M tiles"), (4096, "GroupNorm fused into every halo conv"), (64, "no tap pairing"), (8, "no halo reuse"),
                                        (512, "cluster-2 weight multicast"), (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"), (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"),
                                        (524288, "no GroupNorm fusion")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
