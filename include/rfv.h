@@ -88,6 +88,8 @@ typedef struct {
                                    once per loop for all steps (A/B testing) */
 #define RFV_FLAG_NO_FUSE_GN 524288 /* never apply GroupNorm+SiLU inside the consuming conv (by default the sampling plan does so
                                    on the 32x32 level, where the halo box is only 1.5x the tile and the fused kernel wins) */
+#define RFV_FLAG_NO_WA     1048576 /* 3x3 stride-1 convs at the 32/64/128-pixel levels: do not use the weights-as-A kernel (conv_wa.cuh:
+                                    * A = 128-row weight block, B = up to 256 pixels), fall back to the pixel-major halo kernels (A/B) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

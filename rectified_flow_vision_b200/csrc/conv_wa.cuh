@@ -1,0 +1,485 @@
+// 3x3 stride-1 convolution on tcgen05 with the WEIGHTS as the A operand and up to 256 PIXELS as the B operand.
+//
+// Why: in SS mode an M=128 tcgen05.mma re-reads its 128-row A operand from shared memory in ~82 cycles whatever N is
+// (tools/micro/umma_rate2.cu: N=64 82.8, N=128 81.8, N=192 96, N=256 128 cycles per instruction), so the pixel-major
+// halo kernels (conv_halo.cuh: A = 128 positions, B = C_out weights) cannot exceed 39 % of the tensor pipe on 64-channel
+// layers and 78 % on 128-channel ones.  Here the roles are swapped: A = one 128-row weight block (16 KB, K-major), B = N
+// consecutive positions of the flat padded image (the halo box of conv_halo.cuh, same shifted-start-address trick per tap),
+// N = 192..256, which is the shape the pipe runs at full rate.  The accumulator is D[channel (TMEM lane)][position (column)].
+//
+//   * C_out tile = 128: block rows = output channels, nine taps per 64-channel chunk.
+//   * C_out tile = 64 (PAIR): the 128 rows hold TWO taps of the same 64 channels -- within every 16 rows, rows 0-7 are tap
+//     (dy,-1) and rows 8-15 tap (dy,0) of the same 8 channels.  Both halves see the same B operand (start = shift of the first
+//     tap), so the second tap's contribution to position p lands one column to the right: out[p] = top[p] + bot[p+1]; tiles
+//     advance by N-1 positions.  Three pair blocks + three single blocks ((dy,+1), second half zero) per chunk: 6 MMA groups
+//     for 9 taps = 75 % of the pipe (a common column offset admits at most three disjoint pairs in a 3x3 stencil).
+//   * The 1x1 shortcut of a ResidualBlock is extra K chunks at the centre shift (as in conv_halo.cuh); the IDENTITY residual
+//     is one more: a chunk of the residual tensor multiplied by an identity block (exact in fp32 accumulation), so the
+//     epilogue never touches it.
+//   * Epilogue in the m16n8 fragment layout: tcgen05.ld.16x256b gives thread t rows t/4 and t/4+8 of a 16-lane group and
+//     columns 2(t%4), 2(t%4)+1 of every 8-column group.  In PAIR mode both taps of a channel sit in the SAME thread, so the
+//     one-column shift is one in-thread add plus one shuffle per two outputs.  GroupNorm partial sums are per-thread running sums
+//     (channels are lanes) reduced once per tile; the bf16 result is transposed to [pixel][channel] rows with stmatrix.trans
+//     into a per-warp staging buffer and leaves with 16-byte stores (register mapping verified by tools/micro/frag_test.cu).
+//   * FUSE: GroupNorm(+SiLU) is applied to the segment-0 boxes in shared memory by 12 transform warps between the TMA write
+//     and the MMAs (conv_halo_fused.cuh's scheme; coefficients per (image, channel) from gn_coef_kernel).
+//
+//   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-11  epilogue
+//   (FUSE: warps 12-23 transform)
+// Replaces nn.Conv2d call sites models/unet.py:38,41(+51) at the 64x64 / 32x32 (/128x128) levels, and their data gradients.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_params.h"
+
+namespace rfv {
+
+struct WaGeom {
+    int W, H, pitch, rows;        // pitch = W + 1; rows = box height
+    int N, adv;                   // MMA N (positions per tile, multiple of 32) / positions a tile advances by (N or N-1)
+    int tiles_per_img, m_tiles, n_tiles;
+    int cch0, cch0a;              // 64-channel chunks of segment 0 (the first cch0a from map A0, the rest from A0b)
+    int cch1a, cch1b, cchr;       // chunks of the two shortcut sources / of the identity residual (cchr: 0 = none)
+    int slots0;                   // weight blocks per segment-0 chunk: 9, or 6 (PAIR)
+    int nblk;                     // weight blocks per channel tile in the packed buffer (incl. the identity blocks)
+    int box_bytes, stage_bytes;   // rows*pitch*128 / 1024-aligned stage (box + one trailing zero row)
+    int a_stages, w_stages, resident;
+    int ctile;                    // output channels per tile: 128, or 64 (PAIR)
+    uint32_t inv_pitch;           // ceil(2^32 / pitch)
+    uint32_t inv_tpi;             // ceil(2^32 / tiles_per_img)
+};
+
+constexpr int WA_THREADS = 384;         // 4 control + 8 epilogue warps
+constexpr int WA_FUSE_THREADS = 768;    // + 12 transform warps
+constexpr int WA_TWARPS = 12;
+constexpr int WA_BLK = 128 * 128;       // one weight block: 128 rows x 64 bf16
+
+__host__ __device__ constexpr int wa_stage_pitch(bool pair) { return pair ? 48 : 80; }   // bytes per staged pixel row (+16 pad)
+__host__ __device__ constexpr int wa_staging_bytes(bool pair) { return 8 * 32 * wa_stage_pitch(pair); }
+
+// [Cout][Ktot] K-major bf16 (K = tap*C0 + c | K0 + shortcut c)  ->  [n_tiles][nblk][128 rows][64] blocks in consumption order
+__global__ void pack_wa_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Cout, int C0, int K0, int Ktot, int cch0,
+                               int cch1, int cchr, int pair, int n_tiles) {
+    const int slots0 = pair ? 6 : 9;
+    const int nblk = cch0 * slots0 + cch1 + cchr;
+    const size_t total = (size_t)n_tiles * nblk * (WA_BLK / 2);   // elements
+    const bf16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e & 63), r = (int)((e >> 6) & 127);
+        const int blk = (int)((e >> 13) % nblk), nt = (int)((e >> 13) / nblk);
+        int co, half = 0;
+        if (pair) { co = nt * 64 + (r >> 4) * 8 + (r & 7); half = (r >> 3) & 1; }
+        else co = nt * 128 + r;
+        bf16 v = zero;
+        if (blk < cch0 * slots0) {
+            const int ch = blk / slots0, slot = blk - ch * slots0;
+            int tap = slot;
+            if (pair) tap = slot < 3 ? slot * 3 + half : (half ? -1 : (slot - 3) * 3 + 2);
+            if (tap >= 0) v = src[(size_t)co * Ktot + (size_t)tap * C0 + ch * 64 + k];
+        } else if (blk < cch0 * slots0 + cch1) {
+            const int j = blk - cch0 * slots0;
+            if (!half) v = src[(size_t)co * Ktot + K0 + j * 64 + k];
+        } else {
+            const int j = blk - cch0 * slots0 - cch1;
+            const int local = pair ? (r >> 4) * 8 + (r & 7) : r;
+            if (!half && local == j * 64 + k) v = one;
+        }
+        dst[e] = v;
+    }
+}
+
+__device__ __forceinline__ void tmem_ld_16x256_x4(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256_x1(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+
+template <bool PAIR, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? WA_FUSE_THREADS : WA_THREADS, 1)
+conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA0b,
+               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapW, const ConvParams p, const WaGeom g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // [1 KB guard][box ring][weight blocks: ring or resident][epilogue staging: 8 warps][barriers]
+    uint8_t* smem_x = smem + 1024;
+    uint8_t* smem_w = smem_x + (size_t)g.a_stages * g.stage_bytes;
+    const int nchunks = g.cch0 + g.cch1a + g.cch1b + g.cchr;
+    const int nblk_used = g.cch0 * g.slots0 + g.cch1a + g.cch1b + g.cchr;
+    const int w_slots = g.resident ? nblk_used : g.w_stages;
+    uint8_t* smem_o = smem_w + (size_t)w_slots * WA_BLK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + wa_staging_bytes(PAIR));
+    uint64_t* xfull = bars;                       // TMA -> (transform | MMA)
+    uint64_t* xready = xfull + g.a_stages;        // transform -> MMA (FUSE only)
+    uint64_t* xempty = xready + g.a_stages;       // MMA -> TMA
+    uint64_t* wfull = xempty + g.a_stages;        // [w_stages] (slot 0 doubles as "resident weights landed")
+    uint64_t* wempty = wfull + g.w_stages;
+    uint64_t* tfull = wempty + g.w_stages;        // [2] MMA -> epilogue
+    uint64_t* tempty = tfull + 2;                 // [2] epilogue -> MMA (8 arrivals: one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapW);
+        for (int s = 0; s < g.a_stages; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xready[s], WA_TWARPS); mbar_init(&xempty[s], 1); }
+        for (int s = 0; s < g.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        mbar_fence_init();
+    }
+    // the row after each box must read as zero (tap (+1,+1) of the last position of the last box row lands there)
+    if (threadIdx.x < 32)
+        for (int s = 0; s < g.a_stages; ++s)
+            reinterpret_cast<uint32_t*>(smem_x + (size_t)s * g.stage_bytes + g.box_bytes)[threadIdx.x] = 0u;
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = g.m_tiles * g.n_tiles;
+
+    if (warp < 4) {
+        if (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == 0) {
+            // ===================== box producer: one halo box per (tile, 64-channel chunk) =====================
+            uint32_t st = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int mt = tile, nt = 0;
+                if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
+                const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
+                const int rbox = (int)__umulhi((uint32_t)(ti * g.adv), g.inv_pitch) - 1;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    mbar_wait(&xempty[st], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&xfull[st], g.box_bytes);
+                        uint8_t* dst = smem_x + (size_t)st * g.stage_bytes;
+                        int c = ch;
+                        if (c < g.cch0a) tma_load_4d(dst, &mapA0, &xfull[st], c * 64, -1, rbox, n);
+                        else if (c < g.cch0) tma_load_4d(dst, &mapA0b, &xfull[st], (c - g.cch0a) * 64, -1, rbox, n);
+                        else if ((c -= g.cch0) < g.cch1a) tma_load_4d(dst, &mapA1, &xfull[st], c * 64, -1, rbox, n);
+                        else if ((c -= g.cch1a) < g.cch1b) tma_load_4d(dst, &mapA2, &xfull[st], c * 64, -1, rbox, n);
+                        else tma_load_4d(dst, &mapR, &xfull[st], nt * g.ctile + (c - g.cch1b) * 64, -1, rbox, n);
+                    }
+                    __syncwarp();
+                    if (++st == (uint32_t)g.a_stages) { st = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 3) {
+            // ===================== weight producer: 16 KB blocks in consumption order =====================
+            if (g.resident) {
+                if ((int)blockIdx.x < total_tiles && elect_one()) {
+                    mbar_arrive_expect_tx(&wfull[0], nblk_used * WA_BLK);
+                    for (int b = 0; b < nblk_used; ++b) tma_load_2d(smem_w + (size_t)b * WA_BLK, &mapW, &wfull[0], 0, b * 128);
+                }
+            } else {
+                uint32_t st = 0, ph = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int nt = tile % g.n_tiles;
+                    for (int b = 0; b < nblk_used; ++b) {
+                        mbar_wait(&wempty[st], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&wfull[st], WA_BLK);
+                            tma_load_2d(smem_w + (size_t)st * WA_BLK, &mapW, &wfull[st], 0, (nt * g.nblk + b) * 128);
+                        }
+                        __syncwarp();
+                        if (++st == (uint32_t)g.w_stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+            const uint32_t idesc = umma_idesc_bf16(128, g.N);
+            uint32_t xst = 0, xph = 0, wst = 0, wph = 0, it = 0;
+            if (g.resident && (int)blockIdx.x < total_tiles) mbar_wait(&wfull[0], 0);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int mt = g.n_tiles > 1 ? tile / g.n_tiles : tile;
+                const int ti = mt - (int)__umulhi((uint32_t)mt, g.inv_tpi) * g.tiles_per_img;
+                const int q0 = ti * g.adv;
+                const int idx0 = q0 - ((int)__umulhi((uint32_t)q0, g.inv_pitch) - 1) * g.pitch;   // row (128 B) of position q0 inside the box buffer
+                const uint32_t as = it & 1;
+                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                int blk = 0;
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const bool seg0 = ch < g.cch0;
+                    mbar_wait(FUSE ? &xready[xst] : &xfull[xst], xph);   // FUSE: the transform warps pass every chunk on
+                    tc_fence_after();
+                    const uint32_t xbase = smem_u32(smem_x + (size_t)xst * g.stage_bytes) + (uint32_t)(idx0 * 128);
+                    const int nslots = seg0 ? g.slots0 : 1;
+                    for (int sl = 0; sl < nslots; ++sl, ++blk) {
+                        int shift = 0;
+                        if (seg0) {
+                            if (PAIR) shift = sl < 3 ? (sl - 1) * g.pitch - 1 : (sl - 4) * g.pitch + 1;
+                            else shift = (sl / 3 - 1) * g.pitch + (sl % 3 - 1);
+                        }
+                        uint32_t wslot = (uint32_t)blk;
+                        if (!g.resident) {
+                            mbar_wait(&wfull[wst], wph);
+                            tc_fence_after();
+                            wslot = wst;
+                        }
+                        if (elect_one()) {
+                            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_w + (size_t)wslot * WA_BLK));
+                            const uint64_t bdesc = umma_desc_sw128(xbase + (uint32_t)(shift * 128));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (ch | sl | j) != 0);
+                            if (!g.resident) umma_commit(&wempty[wst]);
+                            if (sl == nslots - 1) {
+                                umma_commit(&xempty[xst]);
+                                if (ch == nchunks - 1) umma_commit(&tfull[as]);
+                            }
+                        }
+                        __syncwarp();
+                        if (!g.resident && ++wst == (uint32_t)g.w_stages) { wst = 0; wph ^= 1; }
+                    }
+                    if (++xst == (uint32_t)g.a_stages) { xst = 0; xph ^= 1; }
+                }
+            }
+        }
+    } else if (FUSE && warp >= 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===================== transform: GroupNorm(+SiLU) in place on every segment-0 box =====================
+        const int tt = threadIdx.x - 12 * 32;
+        constexpr int PL = WA_TWARPS * 4;              // position lanes
+        const int j = tt & 7, pl = tt >> 3;            // logical 16-byte vector (8 channels) / position lane
+        const int npos = g.rows * g.pitch;
+        uint32_t st = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = g.n_tiles > 1 ? tile / g.n_tiles : tile;
+            const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
+            const int rbox = (int)__umulhi((uint32_t)(ti * g.adv), g.inv_pitch) - 1;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                if (ch < g.cch0) {
+                    float sc[8], sh[8];
+                    const float4* cp = reinterpret_cast<const float4*>(p.gn_coef + ((size_t)n * p.gn_C + ch * 64 + j * 8) * 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = cp[i];
+                        sc[2 * i] = v.x; sh[2 * i] = v.y; sc[2 * i + 1] = v.z; sh[2 * i + 1] = v.w;
+                    }
+                    if (p.gn_silu) {   // silu(y) = h (1 + tanh h), h = y / 2: one MUFU op per element
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { sc[i] *= 0.5f; sh[i] *= 0.5f; }
+                    }
+                    mbar_wait(&xfull[st], ph);
+                    // stage buffers are 1024-byte aligned and PL is a multiple of 8: the swizzle term j ^ (position & 7) of this
+                    // thread's vector is the same for every position it visits
+                    const uint32_t base = smem_u32(smem_x + (size_t)st * g.stage_bytes);
+                    const int row_lo = max(0, -rbox), row_hi = min(g.rows, g.H - rbox);   // box rows inside the image
+                    uint32_t addr = base + (uint32_t)pl * 128 + (uint32_t)((j ^ (pl & 7)) << 4);
+                    int rb = pl / g.pitch, cb = pl - rb * g.pitch;
+                    auto advance = [&](int& r_, int& c_) {
+                        c_ += PL;
+                        while (c_ >= g.pitch) { c_ -= g.pitch; ++r_; }
+                    };
+                    auto xform = [&](uint4& q) {
+                        float f[8];
+                        unpack8(q, f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float y = fmaf(f[i], sc[i], sh[i]);
+                            if (p.gn_silu) {
+                                float t;
+                                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y));
+                                f[i] = fmaf(y, t, y);
+                            } else {
+                                f[i] = y;
+                            }
+                        }
+                        q = pack8(f);
+                    };
+                    for (int pos = pl; pos < npos; pos += 2 * PL, addr += 2 * PL * 128) {
+                        int rb1 = rb, cb1 = cb;
+                        advance(rb1, cb1);
+                        // padding positions (column 0, rows outside the image) stay zero
+                        const bool v0 = cb >= 1 && rb >= row_lo && rb < row_hi;
+                        const bool v1 = pos + PL < npos && cb1 >= 1 && rb1 >= row_lo && rb1 < row_hi;
+                        uint4 q0, q1;
+                        if (v0) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "r"(addr));
+                        if (v1) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "r"(addr + PL * 128));
+                        if (v0) xform(q0);
+                        if (v1) xform(q1);
+                        if (v0) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q0.x), "r"(q0.y), "r"(q0.z), "r"(q0.w) : "memory");
+                        if (v1) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr + PL * 128), "r"(q1.x), "r"(q1.y), "r"(q1.z), "r"(q1.w) : "memory");
+                        rb = rb1; cb = cb1;
+                        advance(rb, cb);
+                    }
+                    fence_async_smem();   // generic writes -> visible to the UMMA reads
+                } else {
+                    mbar_wait(&xfull[st], ph);   // shortcut / residual chunks pass through untouched
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xready[st]);
+                if (++st == (uint32_t)g.a_stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        if (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        // ===================== epilogue: all eight warps drain one accumulator stage =====================
+        // warp quarter q = TMEM lanes 32q..32q+31; the two warps of a quarter take the even / odd 32-column units.
+        // The loop is ISSUE-bound (ncu, first version: 8.7 k warp-instructions per 192-column PAIR tile against 2.3 k cycles of
+        // MMAs), so per-column bookkeeping is done once per unit with lane = column (one ballot gives the validity mask, one
+        // shuffle per stored row gives its pixel offset) and the statistics are reduced with the transposing butterfly.
+        const int q = warp & 3, uh = (warp - 4) >> 2;
+        const int t4 = lane & 3, t8 = lane >> 2;
+        constexpr int SP = wa_stage_pitch(PAIR);
+        constexpr int CV = PAIR ? 2 : 4;                     // channel sub-blocks of 8 per thread
+        const uint32_t stage = smem_u32(smem_o + (warp - 4) * 32 * SP);
+        const int nunits = g.N >> 5;
+        const int HW = g.H * g.W;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int mt = tile, nt = 0;
+            if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
+            const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
+            const int q0 = ti * g.adv;
+            const int cbase = nt * g.ctile + q * (PAIR ? 16 : 32);   // first channel of this warp
+            bf16* const obase = p.out + (size_t)n * HW * p.Cout + cbase;
+            // per-thread channels: cbase + 8*v + t8, v = 0..CV-1 (fragment rows t8 / t8+8 of the two 16-lane halves)
+            float addv[CV], s1[CV], s2[CV];
+            {
+                const float* ab = p.temb ? p.temb + (size_t)n * p.temb_stride : p.bias;
+#pragma unroll
+                for (int v = 0; v < CV; ++v) { addv[v] = ab[cbase + 8 * v + t8]; s1[v] = 0.f; s2[v] = 0.f; }
+            }
+            const uint32_t as = it & 1;
+            mbar_wait(&tfull[as], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            if (uh >= nunits) {   // (never with N >= 64; keeps the barrier protocol total)
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+            for (int u = uh; u < nunits; u += 2) {
+                const int col0 = u * 32;
+                uint32_t r[2][16];
+                uint32_t nx[2][4];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) tmem_ld_16x256_x4(tbase + ((uint32_t)(hh * 16) << 16) + col0, r[hh]);
+                if (PAIR) {
+                    const int cn = min(col0 + 32, g.N - 8);   // first group of the next unit (the tile's last column pairs with nothing)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) tmem_ld_16x256_x1(tbase + ((uint32_t)(hh * 16) << 16) + cn, nx[hh]);
+                }
+                // lane = column of the unit: validity and pixel offset inside the image (overlaps the TMEM load latency)
+                const int pos_l = q0 + col0 + lane;
+                const int rr_l = (int)__umulhi((uint32_t)pos_l, g.inv_pitch);
+                const bool ok_l = pos_l - rr_l * g.pitch >= 1 && rr_l < g.H && col0 + lane < g.adv;
+                const uint32_t vmask = __ballot_sync(0xffffffffu, ok_l);
+                const int pixoff_l = pos_l - rr_l - 1;
+                const uint32_t m2 = vmask >> (2 * t4);
+                tmem_ld_wait();
+                if (u + 2 >= nunits) {   // this warp's last unit: its share of the stage is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                uint32_t mprev[2] = {0u, 0u};
+#pragma unroll
+                for (int gp = 0; gp < 4; ++gp) {
+                    const bool vA = (m2 & (1u << (8 * gp))) != 0, vB = (m2 & (2u << (8 * gp))) != 0;
+                    uint32_t m[4];
+                    if (PAIR) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float a0 = __uint_as_float(r[hh][4 * gp]), a1 = __uint_as_float(r[hh][4 * gp + 1]);
+                            const float b0 = __uint_as_float(r[hh][4 * gp + 2]), b1 = __uint_as_float(r[hh][4 * gp + 3]);
+                            const float b0n = __uint_as_float(gp < 3 ? r[hh][4 * gp + 6] : nx[hh][2]);   // b0 of the next column group
+                            const float send = t4 == 0 ? b0n : b0;
+                            const float got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((lane + 1) & 3));
+                            const float oA = a0 + b1 + addv[hh], oB = a1 + got + addv[hh];
+                            const float xA = vA ? oA : 0.f, xB = vB ? oB : 0.f;
+                            s1[hh] += xA + xB;
+                            s2[hh] = fmaf(xA, xA, fmaf(xB, xB, s2[hh]));
+                            m[hh] = pack_bf16x2(oA, oB);
+                        }
+                        // two column groups per stmatrix: matrices {gp-1: hh0, hh1, gp: hh0, hh1}
+                        if (gp & 1) {
+                            const uint32_t a = stage + (uint32_t)((8 * (gp - 1 + (lane >> 4)) + (lane & 7)) * SP + ((lane >> 3) & 1) * 16);
+                            stmatrix_x4_trans(a, mprev[0], mprev[1], m[0], m[1]);
+                        } else {
+                            mprev[0] = m[0]; mprev[1] = m[1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const int hh = v >> 1, k = v & 1;
+                            const float oA = __uint_as_float(r[hh][4 * gp + 2 * k]) + addv[v];
+                            const float oB = __uint_as_float(r[hh][4 * gp + 2 * k + 1]) + addv[v];
+                            const float xA = vA ? oA : 0.f, xB = vB ? oB : 0.f;
+                            s1[v] += xA + xB;
+                            s2[v] = fmaf(xA, xA, fmaf(xB, xB, s2[v]));
+                            m[v] = pack_bf16x2(oA, oB);
+                        }
+                        const uint32_t a = stage + (uint32_t)((8 * gp + (lane & 7)) * SP + (lane >> 3) * 16);
+                        stmatrix_x4_trans(a, m[0], m[1], m[2], m[3]);
+                    }
+                }
+                __syncwarp();
+                // copy-out: 32 pixel rows x (CV 16-byte parts); CV consecutive lanes write one pixel's contiguous channels
+#pragma unroll
+                for (int k2 = 0; k2 < CV; ++k2) {
+                    const int px = k2 * (32 / CV) + lane / CV, part = lane % CV;
+                    const int pixoff = __shfl_sync(0xffffffffu, pixoff_l, px);
+                    if ((vmask >> px) & 1u) {
+                        uint4 val;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(stage + (uint32_t)(px * SP + part * 16)));
+                        *reinterpret_cast<uint4*>(obase + (uint32_t)(pixoff * p.Cout + part * 8)) = val;
+                    }
+                }
+                __syncwarp();
+            }
+            if (p.stats) {
+                // transposing butterfly: every value is summed over all 32 lanes (4 column lanes x 8 channels of an 8-block)
+                float t[8];
+#pragma unroll
+                for (int v = 0; v < CV; ++v) { t[2 * v] = s1[v]; t[2 * v + 1] = s2[v]; }
+                int idx;
+                if (PAIR) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = (lane & 16) ? t[i] : t[i + 2], keep = (lane & 16) ? t[i + 2] : t[i];
+                        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                    {
+                        const float send = (lane & 8) ? t[0] : t[1], keep = (lane & 8) ? t[1] : t[0];
+                        t[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 4);
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+                    t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+                    idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+                } else {
+                    warp_reduce8(t, lane);
+                    idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                }
+                if ((lane & (PAIR ? 7 : 3)) == 0) {
+                    float* dst = p.stats + ((size_t)n * (p.Cout >> p.slab_shift) + ((cbase + 8 * (idx >> 1)) >> p.slab_shift)) * 2;
+                    atomicAdd(dst + (idx & 1), t[0]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace rfv

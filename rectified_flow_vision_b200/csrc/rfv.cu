@@ -26,6 +26,7 @@
 #include "conv_halo.cuh"
 #include "conv_halo_pair.cuh"
 #include "conv_halo_fused.cuh"
+#include "conv_wa.cuh"
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
@@ -129,6 +130,8 @@ struct ConvLayer {
     bf16* w = nullptr;
     float* bias = nullptr;  // fused (conv bias + shortcut bias)
     int iw = -1, ib = -1, isw = -1, isb = -1;  // parameter indices (weight, bias, shortcut weight, shortcut bias)
+    bf16* wa = nullptr;                 // weights-as-A block layout (conv_wa.cuh), packed from `w` after every repack
+    std::vector<int> wparams;           // parameters whose repack rewrites `w`
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -145,7 +148,7 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false;
+    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false, use_wa = true;
     int fuse_mode = 1;   // GroupNorm+SiLU inside the consuming conv: 0 never, 1 where measured faster, 2 wherever the kernel applies
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
     int base_offset_mode = 0;
@@ -312,6 +315,8 @@ struct rfv_engine {
             RFV_TRY(add_param(sc_name + ".bias", Cout, &isb));
         }
         l->isw = isw; l->isb = isb;
+        l->wparams.push_back(iw);
+        if (isw >= 0) l->wparams.push_back(isw);
         params[iw].repack = [this, l, iw](cudaStream_t s) {
             if (l->subpixel) pack_upsample_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0);
             else pack_conv_weight_kernel<<<256, 256, 0, s>>>(pf(iw), l->w, l->Cout, l->C0, l->ks * l->ks, l->Ktot, 0);
@@ -444,6 +449,76 @@ struct rfv_engine {
         return 0;
     }
 
+    // Geometry and shared-memory plan of a weights-as-A conv (conv_wa.cuh).  Picks the tile width N (positions per tile) that
+    // wastes the fewest MMA columns among those that keep the whole weight matrix resident; layers that have to stream their
+    // weights take the widest tiles (weight blocks are re-fetched per tile).
+    int plan_wa(WaGeom* gp, size_t* smem, const ConvLayer* L, int W, int H, bool may_resid, int cch0a) {
+        WaGeom& g = *gp;
+        const bool pair = L->Cout % 128 != 0;
+        g.W = W; g.H = H; g.pitch = W + 1;
+        g.ctile = pair ? 64 : 128;
+        g.n_tiles = L->Cout / g.ctile;
+        g.slots0 = pair ? 6 : 9;
+        g.cch0 = L->C0 / 64; g.cch0a = cch0a; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
+        g.cchr = 0;   // set per launch
+        g.nblk = g.cch0 * g.slots0 + g.cch1a + g.cch1b + g.ctile / 64;
+        g.inv_pitch = (uint32_t)((0x100000000ull + g.pitch - 1) / g.pitch);
+        const int nblk_max = g.nblk - (may_resid ? 0 : g.ctile / 64);
+        const int avail = 227 * 1024 - 2048 - 512 - wa_staging_bytes(pair);
+        const int positions = H * g.pitch;
+        double best = 1e30;
+        int bestN = 0;
+        bool best_res = false;
+        auto shape = [&](int N) {
+            g.N = N; g.adv = N - (pair ? 1 : 0);
+            g.tiles_per_img = (positions + g.adv - 1) / g.adv;
+            g.rows = (g.pitch - 1 + N - 1) / g.pitch + 3;
+            g.box_bytes = g.rows * g.pitch * 128;
+            g.stage_bytes = (g.box_bytes + 128 + 1023) & ~1023;
+        };
+        for (int N = 256; N >= 128; N -= 32) {
+            shape(N);
+            const bool res = g.n_tiles == 1 && (long)nblk_max * WA_BLK + 2L * g.stage_bytes <= avail;
+            if (!res && 3L * WA_BLK + 2L * g.stage_bytes > avail) continue;
+            // streamed weights: every tile re-fetches the whole matrix, so narrow tiles cost L2 bandwidth on top of the columns
+            const double cost = (double)g.tiles_per_img * N / positions * (res ? 1.0 : 1.0 + 0.25 * (256 - N) / 32.0);
+            if ((res && !best_res) || (res == best_res && cost < best - 1e-9)) { best = cost; bestN = N; best_res = res; }
+        }
+        if (!bestN) return fail(RFV_ERR_INVALID, "conv %s: weights-as-A tile does not fit shared memory", L->name.c_str());
+        if (const char* ev = getenv("RFV_WA_N")) { if (!best_res && atoi(ev) >= 128) bestN = atoi(ev); }   // experiments
+        shape(bestN);
+        g.inv_tpi = (uint32_t)((0x100000000ull + g.tiles_per_img - 1) / g.tiles_per_img);
+        g.resident = best_res ? 1 : 0;
+        int wregion;
+        if (g.resident) { g.w_stages = 1; wregion = nblk_max * WA_BLK; g.a_stages = std::min(4, (avail - wregion) / g.stage_bytes); }
+        else {
+            g.w_stages = 6;
+            while (g.w_stages > 3 && (avail - g.w_stages * WA_BLK) / g.stage_bytes < (g.w_stages > 4 ? 3 : 2)) --g.w_stages;
+            if (const char* ev = getenv("RFV_WA_WST")) { if (atoi(ev) >= 2 && (avail - atoi(ev) * WA_BLK) / g.stage_bytes >= 2) g.w_stages = atoi(ev); }
+            wregion = g.w_stages * WA_BLK;
+            g.a_stages = std::min(4, (avail - wregion) / g.stage_bytes);
+        }
+        if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: weights-as-A tile does not fit shared memory", L->name.c_str());
+        *smem = 2048 + (size_t)g.a_stages * g.stage_bytes + wregion + wa_staging_bytes(pair) + 512;
+        return 0;
+    }
+    // allocate the block-layout weight copy of a layer and chain its refresh behind the repack of the parameters it derives from
+    int ensure_wa(ConvLayer* L, const WaGeom& g) {
+        if (L->wa) return 0;
+        RFV_TRY(dalloc(&L->wa, (size_t)g.n_tiles * g.nblk * (WA_BLK / 2)));
+        const int pair = g.ctile == 64 ? 1 : 0, cch1 = g.cch1a + g.cch1b, cchr = g.ctile / 64, cch0 = g.cch0, n_tiles = g.n_tiles;
+        for (int pi : L->wparams) {
+            auto prev = params[pi].repack;
+            params[pi].repack = [this, prev, L, pair, cch0, cch1, cchr, n_tiles](cudaStream_t s) {
+                const int rc = prev ? prev(s) : 0;
+                if (rc) return rc;
+                pack_wa_kernel<<<256, 256, 0, s>>>(L->w, L->wa, L->Cout, L->C0, L->K0, L->Ktot, cch0, cch1, cchr, pair, n_tiles);
+                return cudaGetLastError() == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "weights-as-A pack launch failed");
+            };
+        }
+        return 0;
+    }
+
     int conv_op(ConvLayer* L, ActP in0, std::vector<ActP> sc, ActP resid, ActP out, int temb_off, bool want_stats,
                 ActP acc_of = nullptr, int acc_k = 0, const FuseReq* fr = nullptr) {
         const std::string pre = rec == &ops ? "conv:" : "bwd:dgrad:";
@@ -473,7 +548,48 @@ struct rfv_engine {
         if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
         const bool halo_ok = umma_ok && use_halo && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
                              (out->W == 32 || out->W == 64 || out->W == 128);
-        if (fr) {
+        const bool wa_ok = halo_ok && use_wa && (!resid || resid->C == L->Cout);
+        if (wa_ok) {
+            // weights-as-A kernel (conv_wa.cuh): N = up to 256 positions per MMA, optional in-kernel GroupNorm on segment 0
+            struct WBundle { CUtensorMap a0, a0b, a1, a2, r, w; WaGeom g; size_t smem; bool pair, fuse; };
+            auto bd = std::make_shared<WBundle>();
+            WaGeom& g = bd->g;
+            bd->pair = L->Cout % 128 != 0;
+            bd->fuse = fr != nullptr;
+            RFV_TRY(plan_wa(&g, &bd->smem, L, out->W, out->H, resid != nullptr || acc_of != nullptr, in0->C / 64));
+            RFV_TRY(ensure_wa(L, g));
+            auto amap = [&](CUtensorMap* m, const ActP& t) {
+                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
+            };
+            RFV_TRY(amap(&bd->a0, in0));
+            bd->a0b = bd->a0; bd->a1 = bd->a0; bd->a2 = bd->a0;
+            if (fr && fr->second) RFV_TRY(amap(&bd->a0b, fr->second));
+            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
+            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
+            RFV_TRY(amap(&bd->r, resid ? resid : out));   // identity residual, or in-place gradient accumulation (acc_of)
+            RFV_TRY(make_map2(&bd->w, L->wa, 64, g.n_tiles * g.nblk * 128, 128));
+            if (fr) { p.gn_coef = fr->coef; p.gn_C = fr->C; p.gn_silu = fr->silu; }
+            const int sms = num_sms, sumC_ = sumC;
+            push("conv_wa", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
+                ConvParams q = p;
+                q.B = rc.B;
+                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
+                q.temb_stride = rc.t ? sumC_ : 0;
+                if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
+                WaGeom g = bd->g;
+                g.cchr = q.resid ? g.ctile / 64 : 0;
+                g.m_tiles = rc.B * g.tiles_per_img;
+                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
+                if (bd->fuse) {
+                    if (bd->pair) conv_wa_kernel<true, true><<<grid, WA_FUSE_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    else conv_wa_kernel<false, true><<<grid, WA_FUSE_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                } else {
+                    if (bd->pair) conv_wa_kernel<true, false><<<grid, WA_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    else conv_wa_kernel<false, false><<<grid, WA_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                }
+                return cudaGetLastError();
+            });
+        } else if (fr) {
             // halo-reuse kernel with GroupNorm(+SiLU) applied to the segment-0 chunks in shared memory (conv_halo_fused.cuh)
             if (!halo_ok) return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
             struct FBundle { CUtensorMap a0, a0b, a1, a2, w, o32, o31; HaloGeom g; int BN; size_t smem; };
@@ -930,6 +1046,7 @@ struct rfv_engine {
         L->bias = zero_bias;
         ConvLayer* l = L.get();
         const int pi = kind == 1 ? src->isw : src->iw;
+        l->wparams.push_back(pi);
         auto prev = params[pi].repack;
         params[pi].repack = [this, prev, l, src, kind, pi, C1](cudaStream_t s) {
             const int rc = prev ? prev(s) : 0;
@@ -1102,6 +1219,10 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_DUAL_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1783,6 +1904,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
     e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
+    e->use_wa = !(cfg->flags & RFV_FLAG_NO_WA);
     e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
     e->fuse_mode = (cfg->flags & RFV_FLAG_FUSE_GN) ? 2 : ((cfg->flags & RFV_FLAG_NO_FUSE_GN) ? 0 : 1);
