@@ -21,11 +21,11 @@
 //     one-column shift is one in-thread add plus one shuffle per two outputs.  GroupNorm partial sums are per-thread running sums
 //     (channels are lanes) reduced once per tile; the bf16 result is transposed to [pixel][channel] rows with stmatrix.trans
 //     into a per-warp staging buffer and leaves with 16-byte stores (register mapping verified by tools/micro/frag_test.cu).
-//   * FUSE: GroupNorm(+SiLU) is applied to the segment-0 boxes in shared memory by 12 transform warps between the TMA write
+//   * FUSE: GroupNorm(+SiLU) is applied to the segment-0 boxes in shared memory by 8 transform warps between the TMA write
 //     and the MMAs (conv_halo_fused.cuh's scheme; coefficients per (image, channel) from gn_coef_kernel).
 //
-//   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-11  epilogue
-//   (FUSE: warps 12-23 transform)
+//   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-15  epilogue
+//   (FUSE: warps 16-23 transform)
 // Replaces nn.Conv2d call sites models/unet.py:38,41(+51) at the 64x64 / 32x32 (/128x128) levels, and their data gradients.
 #pragma once
 #include <cuda.h>
@@ -48,15 +48,20 @@ struct WaGeom {
     int ctile;                    // output channels per tile: 128, or 64 (PAIR)
     uint32_t inv_pitch;           // ceil(2^32 / pitch)
     uint32_t inv_tpi;             // ceil(2^32 / tiles_per_img)
+    int rs;                       // box rows per TMA request (a box is fetched as ceil(rows / rs) requests: one request streams at
+                                  // only ~12 B/clk, several in flight overlap)
+    int dbg;                      // experiments (RFV_WA_DBG): 1 = epilogue only waits / releases, 2 = no MMAs issued, 4 = no global stores,
+                                  // 8 = no TMA loads (barriers only)
 };
 
-constexpr int WA_THREADS = 384;         // 4 control + 8 epilogue warps
-constexpr int WA_FUSE_THREADS = 768;    // + 12 transform warps
-constexpr int WA_TWARPS = 12;
+constexpr int WA_EWARPS = 12;                              // epilogue warps (three per TMEM lane quarter)
+constexpr int WA_THREADS = (4 + WA_EWARPS) * 32;           // 4 control + 12 epilogue warps
+constexpr int WA_TWARPS = 8;                               // transform warps (FUSE)
+constexpr int WA_FUSE_THREADS = WA_THREADS + WA_TWARPS * 32;
 constexpr int WA_BLK = 128 * 128;       // one weight block: 128 rows x 64 bf16
 
 __host__ __device__ constexpr int wa_stage_pitch(bool pair) { return pair ? 48 : 80; }   // bytes per staged pixel row (+16 pad)
-__host__ __device__ constexpr int wa_staging_bytes(bool pair) { return 8 * 32 * wa_stage_pitch(pair); }
+__host__ __device__ constexpr int wa_staging_bytes(bool pair) { return WA_EWARPS * 16 * wa_stage_pitch(pair); }   // 16 pixel rows per warp
 
 // [Cout][Ktot] K-major bf16 (K = tap*C0 + c | K0 + shortcut c)  ->  [n_tiles][nblk][128 rows][64] blocks in consumption order
 __global__ void pack_wa_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Cout, int C0, int K0, int Ktot, int cch0,
@@ -98,6 +103,12 @@ __device__ __forceinline__ void tmem_ld_16x256_x4(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_16x256_x2(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_16x256_x1(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -130,7 +141,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* wfull = xempty + g.a_stages;        // [w_stages] (slot 0 doubles as "resident weights landed")
     uint64_t* wempty = wfull + g.w_stages;
     uint64_t* tfull = wempty + g.w_stages;        // [2] MMA -> epilogue
-    uint64_t* tempty = tfull + 2;                 // [2] epilogue -> MMA (8 arrivals: one per epilogue warp)
+    uint64_t* tempty = tfull + 2;                 // [2] epilogue -> MMA (one arrival per epilogue warp)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +150,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xready[s], WA_TWARPS); mbar_init(&xempty[s], 1); }
         for (int s = 0; s < g.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], WA_EWARPS); }
         mbar_fence_init();
     }
     // the row after each box must read as zero (tap (+1,+1) of the last position of the last box row lands there)
@@ -166,15 +177,19 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int rbox = (int)__umulhi((uint32_t)(ti * g.adv), g.inv_pitch) - 1;
                 for (int ch = 0; ch < nchunks; ++ch) {
                     mbar_wait(&xempty[st], ph ^ 1);
-                    if (elect_one()) {
+                    if (g.dbg & 8) { if (elect_one()) mbar_arrive(&xfull[st]); }
+                    else if (elect_one()) {
                         mbar_arrive_expect_tx(&xfull[st], g.box_bytes);
                         uint8_t* dst = smem_x + (size_t)st * g.stage_bytes;
                         int c = ch;
-                        if (c < g.cch0a) tma_load_4d(dst, &mapA0, &xfull[st], c * 64, -1, rbox, n);
-                        else if (c < g.cch0) tma_load_4d(dst, &mapA0b, &xfull[st], (c - g.cch0a) * 64, -1, rbox, n);
-                        else if ((c -= g.cch0) < g.cch1a) tma_load_4d(dst, &mapA1, &xfull[st], c * 64, -1, rbox, n);
-                        else if ((c -= g.cch1a) < g.cch1b) tma_load_4d(dst, &mapA2, &xfull[st], c * 64, -1, rbox, n);
-                        else tma_load_4d(dst, &mapR, &xfull[st], nt * g.ctile + (c - g.cch1b) * 64, -1, rbox, n);
+                        const CUtensorMap* mp;
+                        if (c < g.cch0a) mp = &mapA0;
+                        else if (c < g.cch0) { mp = &mapA0b; c -= g.cch0a; }
+                        else if ((c -= g.cch0) < g.cch1a) mp = &mapA1;
+                        else if ((c -= g.cch1a) < g.cch1b) mp = &mapA2;
+                        else { mp = &mapR; c = nt * (g.ctile / 64) + (c - g.cch1b); }
+                        for (int r0 = 0; r0 < g.rows; r0 += g.rs)
+                            tma_load_4d(dst + (size_t)r0 * g.pitch * 128, mp, &xfull[st], c * 64, -1, rbox + r0, n);
                     }
                     __syncwarp();
                     if (++st == (uint32_t)g.a_stages) { st = 0; ph ^= 1; }
@@ -193,7 +208,8 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int nt = tile % g.n_tiles;
                     for (int b = 0; b < nblk_used; ++b) {
                         mbar_wait(&wempty[st], ph ^ 1);
-                        if (elect_one()) {
+                        if (g.dbg & 8) { if (elect_one()) mbar_arrive(&wfull[st]); }
+                        else if (elect_one()) {
                             mbar_arrive_expect_tx(&wfull[st], WA_BLK);
                             tma_load_2d(smem_w + (size_t)st * WA_BLK, &mapW, &wfull[st], 0, (nt * g.nblk + b) * 128);
                         }
@@ -239,7 +255,8 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             const uint64_t adesc = umma_desc_sw128(smem_u32(smem_w + (size_t)wslot * WA_BLK));
                             const uint64_t bdesc = umma_desc_sw128(xbase + (uint32_t)(shift * 128));
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (ch | sl | j) != 0);
+                            for (int j = 0; j < 4; ++j)
+                                if (!(g.dbg & 2)) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (ch | sl | j) != 0);
                             if (!g.resident) umma_commit(&wempty[wst]);
                             if (sl == nslots - 1) {
                                 umma_commit(&xempty[xst]);
@@ -253,10 +270,10 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 }
             }
         }
-    } else if (FUSE && warp >= 12) {
+    } else if (FUSE && warp >= 4 + WA_EWARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===================== transform: GroupNorm(+SiLU) in place on every segment-0 box =====================
-        const int tt = threadIdx.x - 12 * 32;
+        const int tt = threadIdx.x - (4 + WA_EWARPS) * 32;
         constexpr int PL = WA_TWARPS * 4;              // position lanes
         const int j = tt & 7, pl = tt >> 3;            // logical 16-byte vector (8 channels) / position lane
         const int npos = g.rows * g.pitch;
@@ -331,18 +348,22 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         }
     } else {
-        if (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        // ===================== epilogue: all eight warps drain one accumulator stage =====================
-        // warp quarter q = TMEM lanes 32q..32q+31; the two warps of a quarter take the even / odd 32-column units.
-        // The loop is ISSUE-bound (ncu, first version: 8.7 k warp-instructions per 192-column PAIR tile against 2.3 k cycles of
-        // MMAs), so per-column bookkeeping is done once per unit with lane = column (one ballot gives the validity mask, one
-        // shuffle per stored row gives its pixel offset) and the statistics are reduced with the transposing butterfly.
-        const int q = warp & 3, uh = (warp - 4) >> 2;
+        // 768 threads x 80 registers = 61,440: control 4 x 32 x 32, transform 8 x 32 x 64, epilogue 12 x 32 x 104 = 60,416
+        if (FUSE) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ===================== epilogue: all twelve warps drain one accumulator stage =====================
+        // warp quarter q = TMEM lanes 32q..32q+31; the three warps of a quarter take 16-column half-units round-robin.
+        // ncu on the first version (8 warps, 32-column units, per-column index arithmetic): 8.7 k warp-instructions per
+        // 192-column PAIR tile against 2.3 k cycles of MMAs, issue slots 52 % busy -> per-column bookkeeping is done once per
+        // half-unit with lane = column (one ballot gives the validity mask, one shuffle per stored row its pixel offset), the
+        // statistics are reduced with the transposing butterfly, and three warps per scheduler hide each other's
+        // TMEM-load -> shuffle -> stmatrix -> copy-out latency chain.
+        const int q = warp & 3, slot = (warp - 4) >> 2;
         const int t4 = lane & 3, t8 = lane >> 2;
         constexpr int SP = wa_stage_pitch(PAIR);
         constexpr int CV = PAIR ? 2 : 4;                     // channel sub-blocks of 8 per thread
-        const uint32_t stage = smem_u32(smem_o + (warp - 4) * 32 * SP);
-        const int nunits = g.N >> 5;
+        constexpr int EQ = WA_EWARPS / 4;                    // warps per quarter
+        const uint32_t stage = smem_u32(smem_o + (warp - 4) * 16 * SP);
+        const int nhu = g.N >> 4;
         const int HW = g.H * g.W;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -363,37 +384,37 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(&tfull[as], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-            if (uh >= nunits) {   // (never with N >= 64; keeps the barrier protocol total)
+            if (slot >= nhu || (g.dbg & 1)) {   // (never with N >= 48; keeps the barrier protocol total)
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            for (int u = uh; u < nunits; u += 2) {
-                const int col0 = u * 32;
-                uint32_t r[2][16];
+            for (int u = (g.dbg & 1) ? nhu : slot; u < nhu; u += EQ) {
+                const int col0 = u * 16;
+                uint32_t r[2][8];
                 uint32_t nx[2][4];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) tmem_ld_16x256_x4(tbase + ((uint32_t)(hh * 16) << 16) + col0, r[hh]);
+                for (int hh = 0; hh < 2; ++hh) tmem_ld_16x256_x2(tbase + ((uint32_t)(hh * 16) << 16) + col0, r[hh]);
                 if (PAIR) {
-                    const int cn = min(col0 + 32, g.N - 8);   // first group of the next unit (the tile's last column pairs with nothing)
+                    const int cn = min(col0 + 16, g.N - 8);   // first group of the next half-unit (the tile's last column pairs with nothing)
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) tmem_ld_16x256_x1(tbase + ((uint32_t)(hh * 16) << 16) + cn, nx[hh]);
                 }
-                // lane = column of the unit: validity and pixel offset inside the image (overlaps the TMEM load latency)
-                const int pos_l = q0 + col0 + lane;
+                // lane & 15 = column of the half-unit: validity and pixel offset inside the image (overlaps the TMEM load latency)
+                const int pos_l = q0 + col0 + (lane & 15);
                 const int rr_l = (int)__umulhi((uint32_t)pos_l, g.inv_pitch);
-                const bool ok_l = pos_l - rr_l * g.pitch >= 1 && rr_l < g.H && col0 + lane < g.adv;
+                const bool ok_l = pos_l - rr_l * g.pitch >= 1 && rr_l < g.H && col0 + (lane & 15) < g.adv;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, ok_l);
                 const int pixoff_l = pos_l - rr_l - 1;
                 const uint32_t m2 = vmask >> (2 * t4);
                 tmem_ld_wait();
-                if (u + 2 >= nunits) {   // this warp's last unit: its share of the stage is in registers
+                if (u + EQ >= nhu) {   // this warp's last half-unit: its share of the stage is in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[as]);
                 }
                 uint32_t mprev[2] = {0u, 0u};
 #pragma unroll
-                for (int gp = 0; gp < 4; ++gp) {
+                for (int gp = 0; gp < 2; ++gp) {
                     const bool vA = (m2 & (1u << (8 * gp))) != 0, vB = (m2 & (2u << (8 * gp))) != 0;
                     uint32_t m[4];
                     if (PAIR) {
@@ -401,7 +422,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         for (int hh = 0; hh < 2; ++hh) {
                             const float a0 = __uint_as_float(r[hh][4 * gp]), a1 = __uint_as_float(r[hh][4 * gp + 1]);
                             const float b0 = __uint_as_float(r[hh][4 * gp + 2]), b1 = __uint_as_float(r[hh][4 * gp + 3]);
-                            const float b0n = __uint_as_float(gp < 3 ? r[hh][4 * gp + 6] : nx[hh][2]);   // b0 of the next column group
+                            const float b0n = __uint_as_float(gp < 1 ? r[hh][4 * gp + 6] : nx[hh][2]);   // b0 of the next column group
                             const float send = t4 == 0 ? b0n : b0;
                             const float got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((lane + 1) & 3));
                             const float oA = a0 + b1 + addv[hh], oB = a1 + got + addv[hh];
@@ -410,9 +431,9 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             s2[hh] = fmaf(xA, xA, fmaf(xB, xB, s2[hh]));
                             m[hh] = pack_bf16x2(oA, oB);
                         }
-                        // two column groups per stmatrix: matrices {gp-1: hh0, hh1, gp: hh0, hh1}
+                        // both column groups in one stmatrix: matrices {gp 0: hh0, hh1, gp 1: hh0, hh1}
                         if (gp & 1) {
-                            const uint32_t a = stage + (uint32_t)((8 * (gp - 1 + (lane >> 4)) + (lane & 7)) * SP + ((lane >> 3) & 1) * 16);
+                            const uint32_t a = stage + (uint32_t)((8 * (lane >> 4) + (lane & 7)) * SP + ((lane >> 3) & 1) * 16);
                             stmatrix_x4_trans(a, mprev[0], mprev[1], m[0], m[1]);
                         } else {
                             mprev[0] = m[0]; mprev[1] = m[1];
@@ -433,12 +454,12 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
                 __syncwarp();
-                // copy-out: 32 pixel rows x (CV 16-byte parts); CV consecutive lanes write one pixel's contiguous channels
+                // copy-out: 16 pixel rows x (CV 16-byte parts); CV consecutive lanes write one pixel's contiguous channels
 #pragma unroll
-                for (int k2 = 0; k2 < CV; ++k2) {
+                for (int k2 = 0; k2 < CV / 2; ++k2) {
                     const int px = k2 * (32 / CV) + lane / CV, part = lane % CV;
                     const int pixoff = __shfl_sync(0xffffffffu, pixoff_l, px);
-                    if ((vmask >> px) & 1u) {
+                    if (((vmask >> px) & 1u) && !(g.dbg & 4)) {
                         uint4 val;
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(stage + (uint32_t)(px * SP + part * 16)));
                         *reinterpret_cast<uint4*>(obase + (uint32_t)(pixoff * p.Cout + part * 8)) = val;

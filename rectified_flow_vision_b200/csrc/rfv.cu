@@ -488,6 +488,9 @@ struct rfv_engine {
         if (const char* ev = getenv("RFV_WA_N")) { if (!best_res && atoi(ev) >= 128) bestN = atoi(ev); }   // experiments
         shape(bestN);
         g.inv_tpi = (uint32_t)((0x100000000ull + g.tiles_per_img - 1) / g.tiles_per_img);
+        g.dbg = getenv("RFV_WA_DBG") ? atoi(getenv("RFV_WA_DBG")) : 0;
+        g.rs = getenv("RFV_WA_RS") ? atoi(getenv("RFV_WA_RS")) : 1;
+        if (g.rs < 1 || g.rows % g.rs != 0) g.rs = 1;   // the requests must tile the box exactly (expect_tx = box_bytes)
         g.resident = best_res ? 1 : 0;
         int wregion;
         if (g.resident) { g.w_stages = 1; wregion = nblk_max * WA_BLK; g.a_stages = std::min(4, (avail - wregion) / g.stage_bytes); }
@@ -559,7 +562,7 @@ struct rfv_engine {
             RFV_TRY(plan_wa(&g, &bd->smem, L, out->W, out->H, resid != nullptr || acc_of != nullptr, in0->C / 64));
             RFV_TRY(ensure_wa(L, g));
             auto amap = [&](CUtensorMap* m, const ActP& t) {
-                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
+                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rs, 1);
             };
             RFV_TRY(amap(&bd->a0, in0));
             bd->a0b = bd->a0; bd->a1 = bd->a0; bd->a2 = bd->a0;

@@ -103,7 +103,11 @@ def test_two_lane_sampling_matches_single_lane(monkeypatch):
     assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
 
 
-@pytest.mark.parametrize("flag,name", [(16, "128-position tiles (no double tiles)"), (128, "dual M tiles"), (4096, "GroupNorm fused into every halo conv"), (64, "no tap pairing"), (8, "no halo reuse"),
+NO_WA = 1048576   # RFV_FLAG_NO_WA: pixel-major halo kernels instead of the weights-as-A kernel
+
+
+@pytest.mark.parametrize("flag,name", [(NO_WA, "pixel-major halo kernels (no weights-as-A)"), (NO_WA | 16, "128-position tiles (no double tiles)"), (128, "dual M tiles"),
+                                       (4096, "GroupNorm fused into every weights-as-A conv"), (NO_WA | 4096, "GroupNorm fused into every halo conv"), (NO_WA | 64, "no tap pairing"), (8, "no halo reuse"),
                                        (512, "cluster-2 weight multicast"), (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"), (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"),
                                        (524288, "no GroupNorm fusion")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
