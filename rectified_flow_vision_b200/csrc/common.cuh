@@ -133,6 +133,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const void* map, uint64_
         : "memory");
 }
 
+// L2 prefetch of a tiled box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_4d(const void* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // Tiled TMA store shared -> global (bulk async-group completion).  Elements of the box beyond the tensor's upper bounds are
 // not written; a NEGATIVE start coordinate, which loads accept, raises "illegal instruction" on a store (measured on B200,
 // tools/micro/tma_store_test.cu).

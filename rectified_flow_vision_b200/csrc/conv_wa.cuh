@@ -15,7 +15,9 @@
 //     for 9 taps = 75 % of the pipe (a common column offset admits at most three disjoint pairs in a 3x3 stencil).
 //   * The 1x1 shortcut of a ResidualBlock is extra K chunks at the centre shift (as in conv_halo.cuh); the IDENTITY residual
 //     is one more: a chunk of the residual tensor multiplied by an identity block (exact in fp32 accumulation), so the
-//     epilogue never touches it.
+//     epilogue never touches it.  (Tried instead: adding the residual in the epilogue from global memory, 2-byte loads in the
+//     fragment layout -- 0.55 ms on a 64->64 layer issued per half-unit, 0.31 ms with L2 prefetch and loads one half-unit
+//     ahead, against 0.24-0.26 ms for the identity chunk: every half-unit exposes a memory latency the MMA path hides.)
 //   * Epilogue in the m16n8 fragment layout: tcgen05.ld.16x256b gives thread t rows t/4 and t/4+8 of a 16-lane group and
 //     columns 2(t%4), 2(t%4)+1 of every 8-column group.  In PAIR mode both taps of a channel sit in the SAME thread, so the
 //     one-column shift is one in-thread add plus one shuffle per two outputs.  GroupNorm partial sums are per-thread running sums
@@ -48,6 +50,8 @@ struct WaGeom {
     int ctile;                    // output channels per tile: 128, or 64 (PAIR)
     uint32_t inv_pitch;           // ceil(2^32 / pitch)
     uint32_t inv_tpi;             // ceil(2^32 / tiles_per_img)
+    int tstages, tstride;         // accumulator stages in TMEM (2, or 3 when N <= 160) and their column stride
+    int pf;                       // L2 prefetch distance in tiles (0 = off)
     int rs;                       // box rows per TMA request (a box is fetched as ceil(rows / rs) requests: one request streams at
                                   // only ~12 B/clk, several in flight overlap)
     int dbg;                      // experiments (RFV_WA_DBG): 1 = epilogue only waits / releases, 2 = no MMAs issued, 4 = no global stores,
@@ -140,9 +144,9 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* xempty = xready + g.a_stages;       // MMA -> TMA
     uint64_t* wfull = xempty + g.a_stages;        // [w_stages] (slot 0 doubles as "resident weights landed")
     uint64_t* wempty = wfull + g.w_stages;
-    uint64_t* tfull = wempty + g.w_stages;        // [2] MMA -> epilogue
-    uint64_t* tempty = tfull + 2;                 // [2] epilogue -> MMA (one arrival per epilogue warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tfull = wempty + g.w_stages;        // [<= 4] MMA -> epilogue
+    uint64_t* tempty = tfull + 4;                 // [<= 4] epilogue -> MMA (one arrival per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -150,7 +154,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xready[s], WA_TWARPS); mbar_init(&xempty[s], 1); }
         for (int s = 0; s < g.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], WA_EWARPS); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], WA_EWARPS); }
         mbar_fence_init();
     }
     // the row after each box must read as zero (tap (+1,+1) of the last position of the last box row lands there)
@@ -175,6 +179,28 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
                 const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
                 const int rbox = (int)__umulhi((uint32_t)(ti * g.adv), g.inv_pitch) - 1;
+                if (g.pf > 0) {
+                    // L2 prefetch of the boxes of the tile this CTA runs g.pf iterations from now: the ring only keeps one or two
+                    // boxes in flight, and a box that misses L2 streams in at ~20 B/clk (measured: loads alone take 1.3 us per 50 KB)
+                    const int tp = tile + g.pf * (int)gridDim.x;
+                    if (tp < total_tiles && elect_one()) {
+                        int mtp = tp, ntp = 0;
+                        if (g.n_tiles > 1) { mtp = tp / g.n_tiles; ntp = tp - mtp * g.n_tiles; }
+                        const int np = (int)__umulhi((uint32_t)mtp, g.inv_tpi), tip = mtp - np * g.tiles_per_img;
+                        const int rbp = (int)__umulhi((uint32_t)(tip * g.adv), g.inv_pitch) - 1;
+                        for (int ch = 0; ch < nchunks; ++ch) {
+                            int c = ch;
+                            const CUtensorMap* mp;
+                            if (c < g.cch0a) mp = &mapA0;
+                            else if (c < g.cch0) { mp = &mapA0b; c -= g.cch0a; }
+                            else if ((c -= g.cch0) < g.cch1a) mp = &mapA1;
+                            else if ((c -= g.cch1a) < g.cch1b) mp = &mapA2;
+                            else { mp = &mapR; c = ntp * (g.ctile / 64) + (c - g.cch1b); }
+                            for (int r0 = 0; r0 < g.rows; r0 += g.rs) tma_prefetch_4d(mp, c * 64, -1, rbp + r0, np);
+                        }
+                    }
+                    __syncwarp();
+                }
                 for (int ch = 0; ch < nchunks; ++ch) {
                     mbar_wait(&xempty[st], ph ^ 1);
                     if (g.dbg & 8) { if (elect_one()) mbar_arrive(&xfull[st]); }
@@ -221,17 +247,16 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         } else if (warp == 1) {
             // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
             const uint32_t idesc = umma_idesc_bf16(128, g.N);
-            uint32_t xst = 0, xph = 0, wst = 0, wph = 0, it = 0;
+            uint32_t xst = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
             if (g.resident && (int)blockIdx.x < total_tiles) mbar_wait(&wfull[0], 0);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = g.n_tiles > 1 ? tile / g.n_tiles : tile;
                 const int ti = mt - (int)__umulhi((uint32_t)mt, g.inv_tpi) * g.tiles_per_img;
                 const int q0 = ti * g.adv;
                 const int idx0 = q0 - ((int)__umulhi((uint32_t)q0, g.inv_pitch) - 1) * g.pitch;   // row (128 B) of position q0 inside the box buffer
-                const uint32_t as = it & 1;
-                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&tempty[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
+                const uint32_t d_tmem = tmem_base + as * g.tstride;
                 int blk = 0;
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const bool seg0 = ch < g.cch0;
@@ -268,6 +293,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                     if (++xst == (uint32_t)g.a_stages) { xst = 0; xph ^= 1; }
                 }
+                if (++as == (uint32_t)g.tstages) { as = 0; aph ^= 1; }
             }
         }
     } else if (FUSE && warp >= 4 + WA_EWARPS) {
@@ -365,8 +391,8 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t stage = smem_u32(smem_o + (warp - 4) * 16 * SP);
         const int nhu = g.N >> 4;
         const int HW = g.H * g.W;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        uint32_t as = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mt = tile, nt = 0;
             if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
             const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
@@ -380,10 +406,9 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                 for (int v = 0; v < CV; ++v) { addv[v] = ab[cbase + 8 * v + t8]; s1[v] = 0.f; s2[v] = 0.f; }
             }
-            const uint32_t as = it & 1;
-            mbar_wait(&tfull[as], (it >> 1) & 1);
+            mbar_wait(&tfull[as], aph);
             tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * g.tstride;
             if (slot >= nhu || (g.dbg & 1)) {   // (never with N >= 48; keeps the barrier protocol total)
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&tempty[as]);
@@ -496,6 +521,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     atomicAdd(dst + (idx & 1), t[0]);
                 }
             }
+            if (++as == (uint32_t)g.tstages) { as = 0; aph ^= 1; }
         }
     }
     tc_fence_before();

@@ -481,13 +481,25 @@ struct rfv_engine {
             const bool res = g.n_tiles == 1 && (long)nblk_max * WA_BLK + 2L * g.stage_bytes <= avail;
             if (!res && 3L * WA_BLK + 2L * g.stage_bytes > avail) continue;
             // streamed weights: every tile re-fetches the whole matrix, so narrow tiles cost L2 bandwidth on top of the columns
-            const double cost = (double)g.tiles_per_img * N / positions * (res ? 1.0 : 1.0 + 0.25 * (256 - N) / 32.0);
+            // (measured on the 64->64 layers at N = 160 / 192 / 224: a tile costs its columns plus ~0.9 us of fixed time, about the
+            // MMA time of 100 columns)
+            const double cost = (double)g.tiles_per_img * (N + 100) / positions * (res ? 1.0 : 1.0 + 0.25 * (256 - N) / 32.0);
             if ((res && !best_res) || (res == best_res && cost < best - 1e-9)) { best = cost; bestN = N; best_res = res; }
         }
         if (!bestN) return fail(RFV_ERR_INVALID, "conv %s: weights-as-A tile does not fit shared memory", L->name.c_str());
-        if (const char* ev = getenv("RFV_WA_N")) { if (!best_res && atoi(ev) >= 128) bestN = atoi(ev); }   // experiments
+        if (const char* ev = getenv("RFV_WA_N")) {   // experiments
+            const int Ne = atoi(ev);
+            if (Ne >= 128 && Ne <= 256 && Ne % 32 == 0) {
+                shape(Ne);
+                if (!best_res || (long)nblk_max * WA_BLK + 2L * g.stage_bytes <= avail) bestN = Ne;
+            }
+        }
         shape(bestN);
         g.inv_tpi = (uint32_t)((0x100000000ull + g.tiles_per_img - 1) / g.tiles_per_img);
+        g.tstages = g.N <= 128 ? 4 : (g.N <= 160 ? 3 : 2);
+        g.tstride = g.N <= 128 ? 128 : (g.N <= 160 ? 160 : 256);
+        if (getenv("RFV_WA_TST")) { g.tstages = 2; g.tstride = 256; }
+        g.pf = getenv("RFV_WA_PF") ? atoi(getenv("RFV_WA_PF")) : 0;
         g.dbg = getenv("RFV_WA_DBG") ? atoi(getenv("RFV_WA_DBG")) : 0;
         g.rs = getenv("RFV_WA_RS") ? atoi(getenv("RFV_WA_RS")) : 1;
         if (g.rs < 1 || g.rows % g.rs != 0) g.rs = 1;   // the requests must tile the box exactly (expect_tx = box_bytes)
@@ -581,6 +593,7 @@ struct rfv_engine {
                 if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
                 WaGeom g = bd->g;
                 g.cchr = q.resid ? g.ctile / 64 : 0;
+                if (g.cchr && !getenv("RFV_WA_PF")) g.pf = 1;   // two boxes per tile through a short ring: prefetch the next tile's into L2
                 g.m_tiles = rc.B * g.tiles_per_img;
                 const int grid = std::min(g.m_tiles * g.n_tiles, sms);
                 if (bd->fuse) {
