@@ -457,11 +457,12 @@ def run_ours(args):
         for k in kinds.values():
             k["share"] = k["ms"] / tot_ms
         line["kernel_split_ms_per_forward"] = {"micro_batch": mb, **{k: v for k, v in kinds.items()}}
-        tc = {k: kinds[k] for k in ("conv_halo", "conv_umma") if k in kinds}
+        tc = {k: kinds[k] for k in ("conv_wa", "conv_halo", "conv_umma") if k in kinds}
         if tc:
             # dominant kernel = the tcgen05 conv class with the most time in a forward; algorithmic FLOPs (2*MACs,
             # rfv_profile_report) of the convolutions it executed / CUDA-event time of its launches
-            names = {"conv_halo": "conv_halo_kernel<BN> (tcgen05 3x3 convs with halo reuse, all launches of one forward)",
+            names = {"conv_wa": "conv_wa_kernel<PAIR,FUSE> (tcgen05 3x3 convs, weights as the A operand, up to 256 pixels as B; all launches of one forward)",
+                     "conv_halo": "conv_halo_kernel<BN> (tcgen05 3x3 convs with halo reuse, all launches of one forward)",
                      "conv_umma": "conv_umma_kernel<BN> (tcgen05 implicit-GEMM convs, all launches of one forward)"}
             dom = max(tc, key=lambda k: tc[k]["ms"])
             fl = tc[dom]["gflop_per_image"] * 1e9 * mb

@@ -161,6 +161,19 @@ int rfv_zero_grad(rfv_handle h, void* stream);
  * loss of this call.  Batches larger than the micro-batch are processed in chunks (gradient accumulation). */
 int rfv_train_accumulate(rfv_handle h, const float* x0, const float* x1, const float* t, int64_t batch,
                          float dropout_p, uint64_t seed, float* loss_out, void* stream);
+/* The two halves of rfv_train_accumulate for callers that own the loss (the autograd surface of the Python mirror:
+ * UNet.forward in training mode, models/unet.py:229-275 with nn.Dropout active, followed by loss.backward(),
+ * models/base_flow.py:268-270).  rfv_train_forward evaluates v = velocity_net(x, t) in training mode and KEEPS the
+ * activations of this one micro-batch (batch <= micro_batch, else RFV_ERR_STATE); rfv_train_backward takes dL/dv
+ * ([batch,C,S,S] fp32 NCHW device) and ADDS dL/dparam into the flat gradient buffer.  x and t must stay valid until the
+ * backward call (the input conv's weight gradient re-reads them).  Any other compute call on the handle in between
+ * invalidates the kept activations (rfv_train_backward then fails with RFV_ERR_STATE instead of using them). */
+int rfv_train_forward(rfv_handle h, const float* x, const float* t, int64_t batch, float dropout_p, uint64_t seed,
+                      float* v_out, void* stream);
+int rfv_train_backward(rfv_handle h, const float* dv, int64_t batch, void* stream);
+/* Zero the AdamW moments (a fresh torch.optim.AdamW, as every train_* call of the reference builds:
+ * models/rectified_flow.py:208, models/base_flow.py:255).  The step counter lives with the caller (rfv_adamw.step). */
+int rfv_reset_optimizer(rfv_handle h, void* stream);
 /* The flat fp32 gradient buffer (device memory owned by the engine; one slot per parameter tensor in
  * rfv_tensor_info order; conv-weight slots are laid out [O][kh*kw][I]). */
 int rfv_grad_buffer(rfv_handle h, float** dev_ptr, int64_t* numel);

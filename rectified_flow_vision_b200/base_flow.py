@@ -9,9 +9,10 @@ reference (``models/base_flow.py:24-226``); the numerical bodies are single call
   compute_loss           -> rfv_fm_loss         (models/base_flow.py:113-129; forward value only, see below)
   save / load            -> unchanged torch.save / torch.load of {'state_dict','config'} (models/base_flow.py:210-226)
 
-``compute_loss`` returns the loss VALUE (no autograd graph: the backward pass is native too, driven by
-``train_base_flow`` / ``train_rectified_flow`` through ``training.NativeTrainer`` -- rfv_train_accumulate +
-rfv_optimizer_step -- never through PyTorch autograd).
+``train_base_flow`` / ``train_rectified_flow`` drive the native step (``training.NativeTrainer``: rfv_train_accumulate +
+rfv_optimizer_step, no graph).  A caller-written loop over ``compute_loss(x).backward()`` / ``model(x_t, t)`` in training
+mode with any ``torch.optim`` optimizer works too: ``autograd.py`` wraps rfv_train_forward / rfv_train_backward in a
+``torch.autograd.Function`` that fills ``.grad`` of the 174 parameters.
 """
 from __future__ import annotations
 
@@ -52,10 +53,14 @@ class BaseFlowModel(nn.Module):
         return self.velocity_net(x, t)
 
     def compute_loss(self, x1: torch.Tensor) -> torch.Tensor:
-        """Flow-matching loss value for a data batch (models/base_flow.py:104-131): fresh x0 ~ N(0,I),
-        t ~ U[0,1).  Returned tensor carries no autograd graph (training goes through ``train_base_flow``)."""
+        """Flow-matching loss for a data batch (models/base_flow.py:104-131): fresh x0 ~ N(0,I), t ~ U[0,1).
+        In training mode the result carries an autograd graph to every parameter (``loss.backward()`` runs the native
+        backward pass and fills ``.grad``, see ``autograd.py``); in eval mode it is the fused forward-only kernel path."""
         x0 = torch.randn_like(x1)
         t = torch.rand(x1.shape[0], device=x1.device)
+        if self.training:
+            x_t, target = self.get_interpolation(x0, x1, t)
+            return torch.nn.functional.mse_loss(self.forward(x_t, t), target)
         return self._engine(x1.shape[-1]).fm_loss(x0, x1, t)
 
     @torch.no_grad()

@@ -213,6 +213,8 @@ struct rfv_engine {
     cudaGraphExec_t repack_graph = nullptr;
     cudaStream_t s_bwd = nullptr, s_side = nullptr;
     cudaEvent_t ev_bwd[4]{};
+    RunCtx fwd_rc;             // rfv_train_forward's context, replayed by rfv_train_backward
+    bool have_fwd = false;
     bool two_streams = true;   // RFV_FLAG_ONE_STREAM: run the whole backward pass on one stream (A/B testing)
     int norm_sites = 0;
     struct TimeProj { int off, Cout, iw, ib, icb; };
@@ -1762,6 +1764,7 @@ int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
     for (auto& p : params)
         if (!p.loaded) return fail(RFV_ERR_STATE, "parameter %s was never uploaded (rfv_set_tensor)", p.name.c_str());
     if (rc.B < 1 || rc.B > cap) return fail(RFV_ERR_STATE, "micro-batch %d outside [1,%d]", rc.B, cap);
+    have_fwd = false;   // every forward overwrites the activation arena (rfv_train_forward re-arms the flag afterwards)
     if (!rc.temb_only) CU_CHECK(cudaMemsetAsync(stats_arena, 0, stats_used * sizeof(float), s));
     while (profiling && prof_events.size() < ops.size()) {
         cudaEvent_t a, b;
@@ -1982,11 +1985,17 @@ RFV_EXPORT int rfv_set_tensor(rfv_handle h, const char* name, const float* dev_p
     Param& p = h->params[it->second];
     if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
     cudaStream_t s = (cudaStream_t)stream;
-    CU_CHECK(cudaMemcpyAsync(p.f32, dev_ptr, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if (p.repack) RFV_TRY(p.repack(s));
-    p.loaded = true;
-    CU_CHECK(cudaEventRecord(h->ev_weights, s));
-    return 0;
+    RFV_TRY(h->enter(s));   // kernels of an earlier call on another stream may still be reading these weights
+    cudaError_t ce = cudaMemcpyAsync(p.f32, dev_ptr, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    int rc = ce == cudaSuccess ? 0 : fail(RFV_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(ce));
+    if (rc == 0 && p.repack) rc = p.repack(s);
+    if (rc == 0) {
+        p.loaded = true;
+        ce = cudaEventRecord(h->ev_weights, s);
+        if (ce != cudaSuccess) rc = fail(RFV_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(ce));
+    }
+    const int rl = h->leave(s);   // also on failure: whatever was enqueued must order later calls
+    return rc ? rc : rl;
 }
 
 RFV_EXPORT int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream) {
@@ -1997,9 +2006,13 @@ RFV_EXPORT int rfv_get_tensor(rfv_handle h, const char* name, float* dev_ptr, in
     if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements", name, (long long)p.numel);
     if (!p.loaded) return fail(RFV_ERR_STATE, "tensor '%s' not loaded", name);
     cudaStream_t s = (cudaStream_t)stream;
-    if (p.readback) return p.readback(dev_ptr, s);
-    CU_CHECK(cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    return 0;
+    RFV_TRY(h->enter(s));   // an optimizer step enqueued on another stream may still be writing this tensor
+    int rc = 0;
+    if (p.readback) rc = p.readback(dev_ptr, s);
+    else if (cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        rc = fail(RFV_ERR_CUDA, "cudaMemcpyAsync failed");
+    const int rl = h->leave(s);
+    return rc ? rc : rl;
 }
 
 RFV_EXPORT int rfv_get_master(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, void* stream) {
@@ -2009,8 +2022,22 @@ RFV_EXPORT int rfv_get_master(rfv_handle h, const char* name, float* dev_ptr, in
     Param& p = h->params[it->second];
     if (p.numel != numel) return fail(RFV_ERR_INVALID, "tensor '%s': expected %lld elements", name, (long long)p.numel);
     if (!p.loaded) return fail(RFV_ERR_STATE, "tensor '%s' not loaded", name);
-    CU_CHECK(cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return 0;
+    RFV_TRY(h->enter((cudaStream_t)stream));
+    int rc = 0;
+    if (cudaMemcpyAsync(dev_ptr, p.f32, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess)
+        rc = fail(RFV_ERR_CUDA, "cudaMemcpyAsync failed");
+    const int rl = h->leave((cudaStream_t)stream);
+    return rc ? rc : rl;
+}
+
+// dropout seed of micro-batch `idx` of a call: both halves of the caller's seed and the chunk index go through an avalanche
+// mix, so consecutive seeds (the trainer passes its step counter) give unrelated mask streams, not XOR-permutations of one
+static uint32_t mix_seed(uint64_t seed, uint32_t idx) {
+    auto mix = [](uint32_t v) {
+        v ^= v >> 16; v *= 0x85ebca6bu; v ^= v >> 13; v *= 0xc2b2ae35u; v ^= v >> 16;
+        return v;
+    };
+    return mix((uint32_t)seed) ^ mix((uint32_t)(seed >> 32) + 0x9e3779b9u * (idx + 1u));
 }
 
 static size_t image_elems(rfv_handle h) { return (size_t)h->cfg.in_channels * h->cfg.image_size * h->cfg.image_size; }
@@ -2153,12 +2180,58 @@ RFV_EXPORT int rfv_train_accumulate(rfv_handle h, const float* x0, const float* 
         rc.train = true;
         rc.drop_thresh = (uint32_t)std::lround((double)dropout_p * 65536.0);
         rc.drop_scale = rc.drop_thresh ? (float)(1.0 / (1.0 - (double)rc.drop_thresh / 65536.0)) : 1.f;
-        rc.seed = (uint32_t)(seed ^ (seed >> 32)) + (uint32_t)idx * 0x85ebca6bu;
+        rc.seed = mix_seed(seed, (uint32_t)idx);
         RFV_TRY(h->run_forward(rc, s));
         RFV_TRY(h->run_backward(rc, s));
     }
+    h->have_fwd = false;   // the kept activations no longer belong to an rfv_train_forward call
     scale_kernel<<<1, 32, 0, s>>>(loss_out, 1, 1.0f / (float)((double)batch * ie));
     CU_CHECK(cudaGetLastError());
+    return h->leave(s);
+}
+
+RFV_EXPORT int rfv_train_forward(rfv_handle h, const float* x, const float* t, int64_t batch, float dropout_p, uint64_t seed,
+                                 float* v_out, void* stream) {
+    if (!h || !x || !t || !v_out || batch < 1) return fail(RFV_ERR_INVALID, "bad argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    if (batch > h->cap) return fail(RFV_ERR_STATE, "rfv_train_forward keeps the activations of ONE micro-batch: batch %lld > micro_batch %d", (long long)batch, h->cap);
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail(RFV_ERR_INVALID, "dropout probability must be in [0,1)");
+    cudaStream_t s = (cudaStream_t)stream;
+    RFV_TRY(h->enter(s));
+    RunCtx rc;
+    rc.B = (int)batch;
+    rc.x = x; rc.t = t; rc.out = v_out; rc.mode = 0;
+    rc.train = true;
+    rc.drop_thresh = (uint32_t)std::lround((double)dropout_p * 65536.0);
+    rc.drop_scale = rc.drop_thresh ? (float)(1.0 / (1.0 - (double)rc.drop_thresh / 65536.0)) : 1.f;
+    rc.seed = mix_seed(seed, 0u);
+    h->have_fwd = false;
+    RFV_TRY(h->run_forward(rc, s));
+    h->fwd_rc = rc;
+    h->have_fwd = true;
+    return h->leave(s);
+}
+
+RFV_EXPORT int rfv_train_backward(rfv_handle h, const float* dv, int64_t batch, void* stream) {
+    if (!h || !dv) return fail(RFV_ERR_INVALID, "null argument");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    if (!h->have_fwd) return fail(RFV_ERR_STATE, "rfv_train_backward without a preceding rfv_train_forward on this handle");
+    if (batch != h->fwd_rc.B) return fail(RFV_ERR_INVALID, "rfv_train_backward: batch %lld, the forward call had %d", (long long)batch, h->fwd_rc.B);
+    cudaStream_t s = (cudaStream_t)stream;
+    RFV_TRY(h->enter(s));
+    CU_CHECK(cudaMemcpyAsync(h->dv_buf, dv, (size_t)batch * image_elems(h) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    h->have_fwd = false;   // the backward pass consumes (overwrites) the kept activations' gradient slots
+    RFV_TRY(h->run_backward(h->fwd_rc, s));
+    return h->leave(s);
+}
+
+RFV_EXPORT int rfv_reset_optimizer(rfv_handle h, void* stream) {
+    if (!h) return fail(RFV_ERR_INVALID, "null handle");
+    if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
+    cudaStream_t s = (cudaStream_t)stream;
+    RFV_TRY(h->enter(s));
+    CU_CHECK(cudaMemsetAsync(h->mflat, 0, (size_t)h->gtotal * sizeof(float), s));
+    CU_CHECK(cudaMemsetAsync(h->vflat, 0, (size_t)h->gtotal * sizeof(float), s));
     return h->leave(s);
 }
 

@@ -17,7 +17,6 @@ from . import _build
 
 RFV_MAX_LEVELS = 8
 FLAG_NO_UMMA = 1
-FLAG_NO_GRAPH = 2
 FLAG_KEEP_ACTS = 4
 FLAG_TRAIN = 32
 
@@ -63,6 +62,9 @@ SYMBOLS = {
     "rfv_fm_loss": (C.c_int, [_VP, _FP, _FP, _FP, _I64, _FP, _VP]),
     "rfv_zero_grad": (C.c_int, [_VP, _VP]),
     "rfv_train_accumulate": (C.c_int, [_VP, _FP, _FP, _FP, _I64, C.c_float, C.c_uint64, _FP, _VP]),
+    "rfv_train_forward": (C.c_int, [_VP, _FP, _FP, _I64, C.c_float, C.c_uint64, _FP, _VP]),
+    "rfv_train_backward": (C.c_int, [_VP, _FP, _I64, _VP]),
+    "rfv_reset_optimizer": (C.c_int, [_VP, _VP]),
     "rfv_grad_buffer": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_I64)]),
     "rfv_get_grad": (C.c_int, [_VP, C.c_char_p, _FP, _I64, C.c_float, _VP]),
     "rfv_bind_param": (C.c_int, [_VP, C.c_char_p, _FP]),
@@ -219,6 +221,20 @@ class Engine:
             t = t.float()
         return t.contiguous()
 
+    def _images(self, x: torch.Tensor, name: str) -> torch.Tensor:
+        """Validated fp32 device copy of an image batch: the C ABI only receives a row count and reads / writes
+        B * in_channels * S * S floats, so a wrong channel count or a non-square tensor must be stopped here (the
+        reference raises a shape error in its first conv)."""
+        s = self.image_size
+        if x.dim() != 4 or x.shape[0] < 1 or x.shape[1] != self.in_channels or x.shape[2] != s or x.shape[3] != s:
+            raise ValueError(f"{name}: expected shape [B,{self.in_channels},{s},{s}] for this engine, got {tuple(x.shape)}")
+        return self._dev_f32(x, name)
+
+    def _times(self, t: torch.Tensor, batch: int) -> torch.Tensor:
+        if t.dim() != 1 or t.shape[0] != batch:
+            raise ValueError(f"t: expected shape [{batch}], got {tuple(t.shape)}")
+        return self._dev_f32(t, "t")
+
     # ----- weights ---------------------------------------------------------------------------------------
     def sync_weights(self, unet: torch.nn.Module, prefix: str = "velocity_net.") -> None:
         """(Re)upload parameters whose storage or version counter changed since the last upload."""
@@ -249,8 +265,8 @@ class Engine:
 
     # ----- hot path --------------------------------------------------------------------------------------
     def velocity(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        x = self._dev_f32(x, "x")
-        t = self._dev_f32(t, "t")
+        x = self._images(x, "x")
+        t = self._times(t, x.shape[0])
         v = torch.empty_like(x)
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_velocity(self.h, x.data_ptr(), t.data_ptr(), v.data_ptr(), x.shape[0],
@@ -259,7 +275,9 @@ class Engine:
 
     def euler_sample(self, noise: torch.Tensor, num_steps: int, save_every: int = 0):
         """Returns (x_final, traj or None); noise is not modified."""
-        x = self._dev_f32(noise, "noise").clone()
+        if int(num_steps) < 1:
+            raise ValueError("num_steps must be >= 1")
+        x = self._images(noise, "noise").clone()
         traj = None
         tp = None
         if save_every and save_every > 0 and num_steps // save_every > 0:
@@ -301,7 +319,15 @@ class Engine:
         """Host fp32 [N,C,S,S] -> host fp32, H2D/D2H inside (pinned buffers are copied asynchronously)."""
         if noise_host.device.type != "cpu" or noise_host.dtype != torch.float32:
             raise ValueError("noise_host must be a CPU fp32 tensor")
+        s_ = self.image_size
+        if noise_host.dim() != 4 or noise_host.shape[0] < 1 or tuple(noise_host.shape[1:]) != (self.in_channels, s_, s_):
+            raise ValueError(f"noise_host: expected shape [N,{self.in_channels},{s_},{s_}], got {tuple(noise_host.shape)}")
+        if int(num_steps) < 1:
+            raise ValueError("num_steps must be >= 1")
         noise_host = noise_host.contiguous()
+        if out is not None and (out.device.type != "cpu" or out.dtype != torch.float32 or out.shape != noise_host.shape
+                                or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous CPU fp32 tensor of the noise's shape")
         if out is None:
             out = torch.empty_like(noise_host, pin_memory=noise_host.is_pinned())
         n = noise_host.shape[0]
@@ -327,8 +353,12 @@ class Engine:
         return out
 
     def straightness(self, x0: torch.Tensor, x1: torch.Tensor, num_points: int) -> torch.Tensor:
-        x0 = self._dev_f32(x0, "x0")
-        x1 = self._dev_f32(x1, "x1")
+        x0 = self._images(x0, "x0")
+        x1 = self._images(x1, "x1")
+        if x1.shape != x0.shape:
+            raise ValueError(f"shape mismatch: x0 {tuple(x0.shape)}, x1 {tuple(x1.shape)}")
+        if int(num_points) < 1:
+            raise ValueError("num_points must be >= 1")
         out = torch.empty(num_points, dtype=torch.float32, device=x0.device)
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_straightness(self.h, x0.data_ptr(), x1.data_ptr(), x0.shape[0], int(num_points),
@@ -336,9 +366,11 @@ class Engine:
         return out
 
     def fm_loss(self, x0: torch.Tensor, x1: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        x0 = self._dev_f32(x0, "x0")
-        x1 = self._dev_f32(x1, "x1")
-        t = self._dev_f32(t, "t")
+        x0 = self._images(x0, "x0")
+        x1 = self._images(x1, "x1")
+        if x1.shape != x0.shape:
+            raise ValueError(f"shape mismatch: x0 {tuple(x0.shape)}, x1 {tuple(x1.shape)}")
+        t = self._times(t, x0.shape[0])
         out = torch.empty((), dtype=torch.float32, device=x0.device)
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_fm_loss(self.h, x0.data_ptr(), x1.data_ptr(), t.data_ptr(), x0.shape[0],
@@ -354,17 +386,40 @@ class Engine:
                          seed: int = 0) -> torch.Tensor:
         """loss = mean((v((1-t) x0 + t x1, t) - (x1 - x0))^2); parameter gradients are ADDED to the flat
         gradient buffer.  Returns the loss as a 0-dim device tensor (no host sync)."""
-        x0 = self._dev_f32(x0, "x0")
-        x1 = self._dev_f32(x1, "x1")
-        t = self._dev_f32(t, "t")
-        if x0.shape != x1.shape or t.shape[0] != x0.shape[0]:
-            raise ValueError(f"shape mismatch: x0 {tuple(x0.shape)}, x1 {tuple(x1.shape)}, t {tuple(t.shape)}")
+        x0 = self._images(x0, "x0")
+        x1 = self._images(x1, "x1")
+        if x0.shape != x1.shape:
+            raise ValueError(f"shape mismatch: x0 {tuple(x0.shape)}, x1 {tuple(x1.shape)}")
+        t = self._times(t, x0.shape[0])
         out = torch.empty((), dtype=torch.float32, device=x0.device)
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_train_accumulate(self.h, x0.data_ptr(), x1.data_ptr(), t.data_ptr(), x0.shape[0],
                                                  float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(),
                                                  self._stream()))
         return out
+
+    def train_forward(self, x: torch.Tensor, t: torch.Tensor, dropout_p: float, seed: int, out: torch.Tensor) -> None:
+        """v = velocity_net(x, t) in training mode for ONE micro-batch, activations kept for ``train_backward``.
+        x, t, out must already be validated fp32 device tensors (``_images`` / ``_times``); x and t must outlive the
+        backward call."""
+        if x.shape[0] > self.micro_batch:
+            raise ValueError(f"train_forward keeps one micro-batch: batch {x.shape[0]} > micro_batch {self.micro_batch}")
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_train_forward(self.h, x.data_ptr(), t.data_ptr(), x.shape[0], float(dropout_p),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(), self._stream()))
+        self.fwd_token = getattr(self, "fwd_token", 0) + 1
+
+    def train_backward(self, dv: torch.Tensor) -> None:
+        """Adds dL/dparam for the micro-batch of the last ``train_forward`` into the flat gradient buffer."""
+        dv = self._images(dv, "dv")
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_train_backward(self.h, dv.data_ptr(), dv.shape[0], self._stream()))
+        self.fwd_token = getattr(self, "fwd_token", 0) + 1   # the kept activations are consumed
+
+    def reset_optimizer(self) -> None:
+        """Zero the AdamW moments (what constructing a fresh torch.optim.AdamW does)."""
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_reset_optimizer(self.h, self._stream()))
 
     def grad_buffer(self) -> torch.Tensor:
         """The engine's flat fp32 gradient buffer as a torch tensor sharing its memory (all-reduce target)."""
@@ -392,6 +447,17 @@ class Engine:
                 raise ValueError(f"{full}: parameters must be contiguous fp32 tensors on {self.device} to be trained")
             _check(self.lib.rfv_bind_param(self.h, full.encode(), p.data_ptr()))
             self._bound.append(p)
+        self._bound_ptrs = [p.data_ptr() for p in self._bound]
+
+    def bound_storage_moved(self) -> bool:
+        """True when a bound Parameter's storage was reallocated since ``bind_params`` (module.to(), p.data = ...): the
+        optimizer would keep writing to the old address."""
+        params = dict(self._bound_module.named_parameters())
+        cur = []
+        for full, _ in self.tensor_names:
+            key = full[len(self._bound_prefix):] if full.startswith(self._bound_prefix) else full
+            cur.append(params[key].data_ptr())
+        return cur != getattr(self, "_bound_ptrs", None)
 
     def optimizer_step(self, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
                        weight_decay: float = 0.01, max_grad_norm: float = 1.0, grad_scale: float = 1.0) -> torch.Tensor:

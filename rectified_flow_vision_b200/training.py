@@ -33,12 +33,19 @@ class NativeTrainer:
         self.lr = float(lr)
         self.betas, self.eps, self.weight_decay, self.max_grad_norm = betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
+        self._fresh = True      # a new trainer = a new torch.optim.AdamW: zero moments on first use of the engine
         self.process_group = process_group
         self._micro_batch = micro_batch
         self.last_grad_norm = None
 
     def _engine(self, size: int):
         return self.model.velocity_net.train_engine(size, torch.device(self.model.device), self._micro_batch)
+
+    def _rank(self) -> int:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.process_group)
+        return 0
 
     def _world(self) -> int:
         import torch.distributed as dist
@@ -53,10 +60,17 @@ class NativeTrainer:
         p = self.model.velocity_net.dropout_p if dropout is None else float(dropout)
         if not self.model.training:
             p = 0.0  # nn.Dropout is the identity in eval mode
+        if self._fresh:
+            # the AdamW moments live in the engine cached on the UNet; every train_* call of the reference builds a new
+            # optimizer with zero state (models/rectified_flow.py:208, models/base_flow.py:255)
+            eng.reset_optimizer()
+            self._fresh = False
         self.step_count += 1
-        eng.zero_grad()
-        loss = eng.train_accumulate(x0, x1, t, dropout_p=p, seed=self.step_count if seed is None else seed)
         world = self._world()
+        if seed is None:   # dropout stream: the step counter, with the rank in the high half (replicas draw different masks)
+            seed = self.step_count | (self._rank() << 32)
+        eng.zero_grad()
+        loss = eng.train_accumulate(x0, x1, t, dropout_p=p, seed=seed)
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(eng.grad_buffer(), op=dist.ReduceOp.SUM, group=self.process_group)

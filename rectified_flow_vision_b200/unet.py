@@ -159,20 +159,26 @@ class UNet(_Node):
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         eng = self._train_engine
-        if eng is None or eng.image_size != image_size or eng.device != dev:
+        if eng is None or eng.image_size != image_size or eng.device != dev or \
+                (micro_batch is not None and micro_batch != eng.micro_batch):
             mb = micro_batch or max(8, (128 * 64 * 64) // (image_size * image_size))
+            self._train_engine = None   # release the old arena before the new one is allocated
+            del eng
             eng = _engine.Engine(self.arch(), image_size, dev, micro_batch=mb, train=True)
             eng.bind_params(self)
             self._train_engine = eng
+        elif eng.bound_storage_moved():
+            eng.bind_params(self)       # parameter storage was reallocated: re-upload and re-bind the write-through pointers
         else:
             eng.sync_weights(self)
         return eng
 
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         if self.training:
-            raise NotImplementedError(
-                "training-mode forward (dropout + autograd) is not part of the native path yet (SURVEY §8 a15) and "
-                "there is no PyTorch fallback; call model.eval() first.")
+            # nn.Dropout active + an autograd edge to every parameter (models/unet.py:62, base_flow.py:268-270): the native
+            # training forward / backward behind a torch.autograd.Function
+            from .autograd import velocity_with_grad
+            return velocity_with_grad(self, x, t)
         if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape [B,{self.in_channels},S,S], got {tuple(x.shape)}")
         if t.dim() != 1 or t.shape[0] != x.shape[0]:

@@ -57,9 +57,10 @@ def test_velocity_vs_reference_and_oracle(case):
     m.eval()
     with torch.no_grad():
         v = m(x, t).cpu().numpy()
-    m.train()
-    with pytest.raises(NotImplementedError):  # no silent PyTorch-autograd fallback for training-mode forward
-        m(x, t)
+    m.train()      # training-mode forward is the native path too (dropout on, autograd.Function): never a PyTorch fallback
+    vt = m(x, t)
+    assert vt.grad_fn is not None and type(vt.grad_fn).__name__.startswith("_VelocityFn")
+    m.eval()
     assert np.isfinite(v).all()
     assert util.rel_l2(v, g["v"]) <= TOL_REF_L2
     assert util.max_rel(v, g["v"]) <= TOL_REF_MAX
