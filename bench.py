@@ -27,10 +27,29 @@ sys.path.insert(0, ROOT)
 
 IMAGE, CH, EULER_STEPS, TOTAL_PAIRS = 64, 3, 100, 65536
 FLOPS_PER_IMG_STEP = 12.7636e9  # SURVEY.md §8d / BASELINE.md §3 (algorithmic, 64x64)
-# DRAM bytes (read + write) of the 16 conv_halo launches of one velocity evaluation, from the `ncu --set full` capture in
-# profiles/r1b_ncu_forward_full.md (micro-batch 256: 4199 MB) -> per image; the bench scales it to its micro-batch.
-NCU_CONV_HALO_DRAM_BYTES_PER_IMAGE = 4199e6 / 256
+# DRAM bytes (read + write) per image of each kernel class in one velocity evaluation, written by tools/ncu_traffic.py from an
+# `ncu --set full` capture of the CURRENT build (the file records the library digest it was captured with).
+NCU_TRAFFIC_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_traffic.json")
 GN_ELEMS_PER_IMAGE = 5013504    # elements normalised per velocity evaluation (30 GroupNorm sites)
+
+
+def ncu_traffic(kind: str, micro_batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one kernel class per forward, from the committed ncu capture; None when
+    the capture is missing or was taken with a different build of the library."""
+    try:
+        with open(NCU_TRAFFIC_FILE) as f:
+            d = json.load(f)
+        from rectified_flow_vision_b200 import _build
+        per_img = d["dram_bytes_per_image"].get(kind)
+        if per_img is None:
+            return None, f"{os.path.basename(NCU_TRAFFIC_FILE)} has no entry for {kind}"
+        note = (f"dram__bytes_read.sum + dram__bytes_write.sum of the {kind} launches of one forward, ncu --set full capture "
+                f"profiles/{os.path.basename(NCU_TRAFFIC_FILE)} (micro-batch {d['micro_batch']}), scaled to micro-batch {micro_batch}")
+        if d.get("library_digest") != _build._digest():
+            note += "; captured with an EARLIER build of the library (kernel sources changed since)"
+        return per_img * micro_batch, note
+    except Exception as ex:  # noqa: BLE001
+        return None, f"no ncu traffic capture available ({type(ex).__name__})"
 
 
 def peaks():
@@ -94,28 +113,43 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (oracle port on the host cores)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_pairs_per_sec(sample_images: int, sample_steps: int, repeats: int = 1):
-    """Time the functional-PyTorch port of the reference path on the host CPU, all threads, on a bounded sample:
+def cpu_pairs_per_sec(sample_images: int, sample_steps: int, repeats: int = 1):
+    """Time the reference's CPU implementation of the path on the host cores, all threads, on a bounded sample:
     `sample_images` noises integrated for `sample_steps` Euler steps (cost is linear in steps -- reference CSV,
-    results/benchmark_results.csv:2-9 -- so pairs/s at 100 steps = images*steps/s / 100)."""
+    results/benchmark_results.csv:2-9 -- so pairs/s at 100 steps = images*steps/s / 100).
+
+    kind "reference": the UNMODIFIED reference package vendored in oracle/_ref (oracle/build_ref.py), driven through its own
+    public API `BaseFlowModel.sample(noise=..., num_steps=...)` (models/base_flow.py:133-177); kind "port": the functional
+    restatement oracle/torch_port.py, only when oracle/_ref was never built."""
     import torch
-    from oracle import torch_port
-    import rectified_flow_vision_b200 as pkg
+    from oracle import build_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    m = pkg.BaseFlowModel(device="cpu")
-    P = {k: v.detach() for k, v in m.state_dict().items()}
     noise = torch.randn(sample_images, CH, IMAGE, IMAGE, generator=torch.Generator().manual_seed(42))
-    torch_port.euler_sample(P, noise[:2], 1)  # warm-up
+    if build_ref.available():
+        ref = build_ref.import_ref()
+        torch.manual_seed(0)
+        m = ref.BaseFlowModel(image_size=IMAGE, device="cpu")
+        m.eval()
+        run, kind = (lambda x, n: m.sample(noise=x, num_steps=n)), "reference"
+        what = "unmodified reference (oracle/_ref, models/base_flow.py BaseFlowModel.sample) on the host CPU, fp32"
+    else:
+        from oracle import torch_port
+        import rectified_flow_vision_b200 as pkg
+        torch.manual_seed(0)
+        m = pkg.BaseFlowModel(device="cpu")
+        P = {k: v.detach() for k, v in m.state_dict().items()}
+        run, kind = (lambda x, n: torch_port.euler_sample(P, x, n)), "port"
+        what = "functional-PyTorch fp32 port of the reference path (oracle/torch_port.py) on the host CPU"
+    run(noise[:2], 1)  # warm-up
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        torch_port.euler_sample(P, noise, sample_steps)
+        run(noise, sample_steps)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     img_steps_per_s = sample_images * sample_steps / best
-    return img_steps_per_s / EULER_STEPS, cores, best
+    return img_steps_per_s / EULER_STEPS, cores, best, kind, what
 
 
 def torch_eager_gpu_image_steps_per_sec(dev, batch: int = 256, steps: int = 2):
@@ -235,20 +269,18 @@ def run_reference(args):
         return
     imgs, steps = 16, 4
     times = []
-    pps = None
     for i in range(args.warmup + args.steps):
-        v, cores, dt = cpu_port_pairs_per_sec(imgs, steps)
+        _, cores, dt, kind, what = cpu_pairs_per_sec(imgs, steps)
         if i >= args.warmup:
             times.append(dt)
-            pps = v if pps is None else max(pps, v)
     mean_dt = sum(times) / len(times)
     value = (imgs * steps / mean_dt) / EULER_STEPS
-    sample = f"{imgs} seeded noises x {steps} Euler steps per step, scaled linearly to {EULER_STEPS} steps"
+    sample = f"{imgs} seeded noises x {steps} Euler steps per step, scaled linearly to {EULER_STEPS} steps; {what}"
     line = {"impl": "reference", "metric": "reflow_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, default_mb()),
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -264,7 +296,8 @@ def workload_config(args, micro_batch):
                         f"{TOTAL_PAIRS}-pair job, batch-sharded over {args.gpus} GPU(s)",
             "pairs_per_step_per_gpu": args.pairs_per_step, "euler_steps": EULER_STEPS, "image": [CH, IMAGE, IMAGE],
             "micro_batch": micro_batch, "parallelism": f"dp{args.gpus} (batch shards, no data-path collective)",
-            "l2_policy": "inputs larger than L2: per-step activation traffic >> 126 MB; fresh noise buffer each step"}
+            "l2_policy": "inputs larger than L2: every Euler step streams > 2 GB of activations per micro-batch (L2 = 126 MB); the "
+                         "noise comes from 4 rotating 100 MB buffers"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -328,7 +361,7 @@ def run_ours(args):
     value = world * P * args.steps / (ms / 1e3)
 
     # ---- e2e: the public API with host buffers (H2D + D2H inside the timed region) ----
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 6))
     out = pkg.generate_reflow_pairs(model, num_pairs=P, num_steps=EULER_STEPS, noise=host_noise[0])  # warm
     barrier()
     t0 = time.perf_counter()
@@ -339,6 +372,59 @@ def run_ours(args):
     barrier()
     e2e_value = world * P * e2e_steps / e2e_s
     img_bytes = P * CH * IMAGE * IMAGE * 4
+    del out, x0, x1
+
+    # ---- e2e with the job's final gather (N > 1): every rank integrates its shard of ONE host-seeded noise tensor and the
+    #      results are all-gathered over NCCL into row order on every rank's host (dist.generate_reflow_pairs_sharded) ----
+    e2e_gather = None
+    if world > 1:
+        from rectified_flow_vision_b200 import dist as rdist
+        job_noise = rdist.seeded_noise(world * P, CH, IMAGE, IMAGE, seed=4242).pin_memory()   # identical on every rank
+        rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True)   # warm (NCCL channels)
+        barrier()
+        t0 = time.perf_counter()
+        g_steps = max(1, min(args.steps, 2))
+        for _ in range(g_steps):
+            gx0, gx1 = rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True)
+        torch.cuda.synchronize()
+        g_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert gx1.shape[0] == world * P
+        e2e_gather = {"value": world * P * g_steps / g_s, "unit": "pairs/s", "steps": g_steps,
+                      "all_gather_bytes_per_rank_per_step": int(world * img_bytes),
+                      "api": "dist.generate_reflow_pairs_sharded(model, num_pairs, 100, noise=<host tensor>, gather=True): shard -> "
+                             "integrate -> ONE all_gather_into_tensor over NCCL -> full (x0, x1) on every rank's host"}
+        del gx0, gx1, job_noise
+
+    # ---- BASELINE.json configs[4]: the config.yaml UNet at 128x128, seeded random-init weights, 8-step Euler, 128 images per
+    #      GPU (batch 1,024 over 8 GPUs), inputs resident in HBM ----
+    cfg5 = None
+    if not args.no_128:
+        torch.manual_seed(0)
+        m128 = pkg.BaseFlowModel(image_size=128, device=f"cuda:{local}")
+        m128.eval()
+        e128 = m128._engine(128)
+        nz = torch.randn(128, CH, 128, 128, generator=torch.Generator().manual_seed(7 + rank)).to(dev)
+        for _ in range(2):
+            e128.euler_sample(nz, 8)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            e128.euler_sample(nz, 8)
+        b.record()
+        barrier()
+        ms128 = max_over_ranks(a.elapsed_time(b)) / reps
+        fl128 = e128.flops_per_image()
+        pk_ = peaks()
+        tf = 128 * 8 * fl128 / (ms128 / 1e3) / 1e12
+        cfg5 = {"images_per_sec": world * 128 / (ms128 / 1e3), "ms_per_batch": ms128, "batch_per_gpu": 128, "euler_steps": 8,
+                "image": [CH, 128, 128], "gflop_per_image_step": fl128 / 1e9, "tflops_per_gpu": tf,
+                "frac_of_burst": tf / pk_["burst"], "frac_of_sustained": tf / pk_["sustained"],
+                "what": "config.yaml UNet (64 ch, mult [1,2,4], 2 res blocks) at 128x128, seeded random-init weights, 8-step Euler"}
+        del e128, m128, nz
+        torch.cuda.empty_cache()
 
     # ---- reflow training step (BASELINE.json configs[3]): fwd + bwd + clip + AdamW on synthetic pairs, data parallel:
     #      per-GPU batch fixed (weak scaling), ONE all-reduce of the flat fp32 gradient buffer per step over NCCL ----
@@ -432,6 +518,21 @@ def run_ours(args):
                 "achieved_tflops": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world,
                 "of_sustained": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["sustained"],
                 "of_burst": value * EULER_STEPS * FLOPS_PER_IMG_STEP / 1e12 / world / pk["burst"], "peaks": pk["source"]}}
+    if e2e_gather is not None:
+        # N > 1: the headline e2e is the variant that ends with the job's final gather; the per-rank (no collective) number stays
+        line["e2e_no_gather"] = dict(line["e2e"])
+        line["e2e"] = {**e2e_gather, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": int(world * img_bytes)}
+    if cfg5 is not None:
+        line["config5_128x128"] = cfg5
+    summary = {"pairs_per_sec": round(value, 1), "e2e_pairs_per_sec": round(line["e2e"]["value"], 1)}
+    if e2e_gather is not None:
+        summary["e2e_no_gather_pairs_per_sec"] = round(e2e_value, 1)
+    if train is not None:
+        summary.update(train_images_per_sec=round(train["images_per_sec"], 1), train_ms_per_step=round(train["ms_per_step"], 3),
+                       train_allreduce_bytes=train["grad_allreduce_bytes"])
+    if cfg5 is not None:
+        summary.update(cfg5_128px_images_per_sec=round(cfg5["images_per_sec"], 1), cfg5_frac_of_burst=round(cfg5["frac_of_burst"], 3))
+    line["summary"] = summary
     if train is not None:
         line["train_step"] = train
 
@@ -469,15 +570,16 @@ def run_ours(args):
             ach = fl / (tc[dom]["ms"] / 1e3) / 1e12
             fl_all = sum(v["gflop_per_image"] for v in tc.values()) * 1e9 * mb
             ach_all = fl_all / (sum(v["ms"] for v in tc.values()) / 1e3) / 1e12
+            # the split is measured in a 3-forward burst with per-launch events (kernels timed in isolation): burst peak
+            traffic, traffic_note = ncu_traffic(dom, mb)
             line["roofline"] = {"bound": "tensor", "kernel": names[dom],
-                                "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
-                                "frac_of_burst": ach / pk["burst"], "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
-                                "traffic": (NCU_CONV_HALO_DRAM_BYTES_PER_IMAGE * mb if dom == "conv_halo" else None),
-                                "traffic_note": "DRAM read+write bytes of this kernel class per forward from the committed ncu --set full capture "
-                                                "(profiles/r1b_ncu_forward_full.md), scaled from micro-batch 256 to this run's micro-batch",
+                                "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"],
+                                "frac_of_sustained": ach / pk["sustained"],
+                                "peak_source": pk["source"] + " (burst: the split is event-timed per launch in a 3-forward burst)",
+                                "traffic": traffic, "traffic_note": traffic_note,
                                 "flops_per_forward": fl, "ms_per_forward": tc[dom]["ms"],
-                                "all_tcgen05_convs": {"achieved": ach_all, "frac": ach_all / pk["sustained"],
-                                                      "frac_of_burst": ach_all / pk["burst"]}}
+                                "all_tcgen05_convs": {"achieved": ach_all, "frac": ach_all / pk["burst"],
+                                                      "frac_of_sustained": ach_all / pk["sustained"]}}
         if "gn_apply" in kinds:
             # second-largest kernel class, HBM-bound: algorithmic bytes = elements x (2 B read + 2 B written)
             # (bytes of the launches that ran, from the engine's profile report: sites fused into their conv launch nothing)
@@ -505,10 +607,9 @@ def run_ours(args):
         line["sampling_images_per_sec"] = samp
         # ---- CPU baseline: the oracle port on this host's cores, bounded sample ----
         try:
-            v, cores, secs = cpu_port_pairs_per_sec(16, 4)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                    "sample": f"16 seeded noises x 4 Euler steps ({secs:.1f} s), scaled linearly to {EULER_STEPS} steps; "
-                                              "functional-PyTorch fp32 port of the reference path (oracle/torch_port.py)"}
+            v, cores, secs, kind, what = cpu_pairs_per_sec(16, 4)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                    "sample": f"16 seeded noises x 4 Euler steps ({secs:.1f} s), scaled linearly to {EULER_STEPS} steps; {what}"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)}
         try:
@@ -525,6 +626,7 @@ def run_ours(args):
                 train["torch_eager_gpu_baseline"] = torch_eager_gpu_train_images_per_sec(dev)
             except Exception as ex:  # noqa: BLE001
                 train["torch_eager_gpu_baseline"] = {"error": str(ex)[:200]}
+    line["summary_tail"] = line["summary"]   # the same short summary again as the LAST key: log tails keep the end of the line
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -539,6 +641,7 @@ def main():
     ap.add_argument("--pairs-per-step", type=int, default=2048)
     ap.add_argument("--train-batch", type=int, default=256, help="per-GPU batch of the training-step measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-128", action="store_true", help="skip the 128x128 (configs[4]) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

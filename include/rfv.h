@@ -53,27 +53,21 @@ typedef struct {
 } rfv_config;
 
 #define RFV_FLAG_NO_UMMA   1   /* force the mma.sync implicit-GEMM kernel everywhere (debug / A-B testing) */
-#define RFV_FLAG_NO_GRAPH  2   /* launch kernels directly instead of replaying a captured CUDA graph */
+#define RFV_FLAG_ONE_LANE  2   /* rfv_euler_sample / rfv_euler_sample_host: integrate the micro-batches of a large batch one after
+                                  the other on one stream instead of as two alternately enqueued chains on two streams (the second
+                                  chain needs a twin engine: a second activation arena and weight copy, created on first use); A/B */
 #define RFV_FLAG_KEEP_ACTS 4   /* never recycle activation buffers, so rfv_debug_activation can read any layer */
-#define RFV_FLAG_NO_HALO   8   /* do not use the halo-reuse tcgen05 kernel (A/B testing against the per-tap kernel) */
-#define RFV_FLAG_NO_DOUBLE_TILE 16 /* halo-reuse convs with streamed weights: 128-position tiles instead of 256-position double
-                                  tiles (two accumulators per weight block); A/B testing */
 
-#define RFV_FLAG_NO_PAIR   64  /* 64-output-channel 3x3 convs: one tap per MMA (N = 64) instead of two (N = 128); A/B testing */
-#define RFV_FLAG_DUAL      128 /* 256-output-channel convs: share each weight slice between two M tiles (conv_umma_dual_kernel).
-                                  Measured on B200 at micro-batch 256: 1.49 ms vs 1.43 ms for the 18 launches -- the lost
-                                  epilogue overlap costs more than the halved weight traffic gains; off by default. */
 /* bits 8-10 (values 256 / 512 / 1024) are not switches but a field: (flags >> 8) & 7 = CTAs per cluster for TMA weight
  * multicast in the per-tap tcgen05 conv kernel (2 or 4; measured slower than 1 on B200: forward 5.11 / 5.29 / 5.36 ms at
  * cluster 1 / 2 / 4, micro-batch 256). */
 #define RFV_FLAG_ONE_STREAM 2048 /* training: run the whole backward pass on one stream (default: weight / bias gradients on a
                                    second, lower-priority stream so the tcgen05 wgrad kernel overlaps the GroupNorm backward) */
-#define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_halo_fused.cuh: 12 transform
-                                   warps, register budgets re-split with setmaxnreg) in EVERY halo-reuse conv instead of only on
-                                   the 32x32 level.  Parity-green, but slower at 64x64, where the flat 128-position tile needs a
-                                   2.5x halo-redundant box and the transform (issue-bound, ~60 instructions per 8-channel vector)
-                                   outlasts the MMAs: forward 4.72 -> 5.14 ms at micro-batch 256 (4.70 with the default
-                                   selective fusion). */
+#define RFV_FLAG_FUSE_GN   4096 /* apply GroupNorm+SiLU to the conv's operand in shared memory (conv_wa.cuh FUSE: 8 transform warps,
+                                   register budgets re-split with setmaxnreg) in EVERY weights-as-A conv instead of only on the 32x32
+                                   level.  Parity-green, but slower at 64x64, where the transform (issue-bound, ~60 instructions
+                                   per 8-channel vector over a 1.8x halo-redundant box) outlasts the MMAs: forward 8.03 -> 8.47 ms
+                                   at micro-batch 512. */
 #define RFV_FLAG_NO_ATTN_UMMA 8192 /* attention core on the mma.sync kernel even where the tcgen05 one applies (A/B testing) */
 #define RFV_FLAG_GN_BWD_TWO_PASS 16384 /* GroupNorm backward as two streaming passes (reduce, apply) everywhere instead of
                                    the single-pass kernel (A/B testing; the two-pass kernels remain the fallback for pixel counts
@@ -89,7 +83,8 @@ typedef struct {
 #define RFV_FLAG_NO_FUSE_GN 524288 /* never apply GroupNorm+SiLU inside the consuming conv (by default the sampling plan does so
                                    on the 32x32 level, where the halo box is only 1.5x the tile and the fused kernel wins) */
 #define RFV_FLAG_NO_WA     1048576 /* 3x3 stride-1 convs at the 32/64/128-pixel levels: do not use the weights-as-A kernel (conv_wa.cuh:
-                                    * A = 128-row weight block, B = up to 256 pixels), fall back to the pixel-major halo kernels (A/B) */
+                                    * A = 128-row weight block, B = up to 256 pixels), fall back to the per-tap implicit-GEMM kernel
+                                    * (conv_umma.cuh) that serves every other conv shape (A/B) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -5,7 +5,8 @@
 same dictionary keys per step count -- with the per-call batch size exposed as ``batch_size`` (the reference
 hard-codes 4, experiments/benchmark.py:60-61).  ``write_results_csv`` writes the file the reference writes at
 experiments/benchmark.py:252-262: columns ``num_steps,base_time_ms,rect_time_ms,base_img_per_sec,rect_img_per_sec,
-speedup`` so results drop into its ``results/`` layout and plotting code.
+speedup`` so results drop into its ``results/`` layout and plotting code; ``create_summary_report`` writes the
+``benchmark_report.txt`` of utils/visualization.py:210-253 next to it.
 
     python -m rectified_flow_vision_b200.benchmark --out results/benchmark_results.csv [--base ckpt.pt --rect ckpt.pt]
 """
@@ -71,6 +72,38 @@ def write_results_csv(path: str, base_results: List[Dict], rect_results: List[Di
         w.writerows(rows)
 
 
+def summary_report_text(results: Dict) -> str:
+    """The text of ``benchmark_report.txt`` as the reference lays it out (utils/visualization.py:219-251): a speed table with
+    one row per step count (ms per image for both models and their ratio) and the mean / max / min speed-up.  ``results`` is
+    the reference's dictionary: ``{'base_model': [...], 'rectified_model': [...]}`` of ``benchmark_speed`` rows."""
+    rule, thin = "=" * 60, "-" * 40
+    pairs = list(zip(results['base_model'], results['rectified_model']))
+    out = [rule, "BENCHMARK REPORT: FLOW DISTILLATION", rule, "", "SPEED COMPARISON", thin,
+           f"{'Steps':<10} {'Base (ms/img)':<15} {'Rect (ms/img)':<15} {'Speedup':<10}", thin]
+    ratios = []
+    for b, r in pairs:
+        bt, rt = b['time_per_image'] * 1000, r['time_per_image'] * 1000
+        out.append(f"{b['num_steps']:<10} {bt:<15.2f} {rt:<15.2f} {(bt / rt if rt > 0 else 0):<10.2f}x")
+        if r['time_per_image'] > 0:
+            ratios.append(b['time_per_image'] / r['time_per_image'])
+    out += ["", rule, "CONCLUSIONS", thin]
+    if ratios:
+        out += [f"Average speedup: {float(np.mean(ratios)):.2f}x", f"Maximum speedup: {max(ratios):.2f}x",
+                f"Minimum speedup: {min(ratios):.2f}x"]
+    return "\n".join(out) + "\n"
+
+
+def create_summary_report(results: Dict, save_dir: str) -> str:
+    """Writes ``<save_dir>/benchmark_report.txt`` (utils/visualization.py:210-253, the text half; the matplotlib plot of that
+    function is out of scope) and returns its path."""
+    os.makedirs(save_dir, exist_ok=True)
+    path = os.path.join(save_dir, 'benchmark_report.txt')
+    with open(path, 'w') as f:
+        f.write(summary_report_text(results))
+    print(f"Report saved to: {path}")
+    return path
+
+
 def main():
     from . import BaseFlowModel, RectifiedFlowModel
     ap = argparse.ArgumentParser()
@@ -93,6 +126,7 @@ def main():
     br = benchmark_speed(base, a.num_samples, a.steps, a.image_size, dev, batch_size=a.batch_size)
     rr = benchmark_speed(rect, a.num_samples, a.steps, a.image_size, dev, batch_size=a.batch_size)
     write_results_csv(a.out, br, rr)
+    create_summary_report({'base_model': br, 'rectified_model': rr}, os.path.dirname(a.out) or '.')
     for row in results_table(br, rr):
         print(row)
 

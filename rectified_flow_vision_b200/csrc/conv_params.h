@@ -30,7 +30,7 @@ struct ConvParams {
     int K0, Ktot;
     int temb_stride;
     int slab_shift;
-    // fused GroupNorm(+SiLU) on the segment-0 operand (conv_halo_fused.cuh): per-(image, channel) scale / shift pairs
+    // fused GroupNorm(+SiLU) on the segment-0 operand (conv_wa.cuh, FUSE): per-(image, channel) scale / shift pairs
     const float* gn_coef;        // [B][gn_C][2] or nullptr
     int gn_C;
     int gn_silu;

@@ -222,145 +222,4 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// BN = 256 convolutions at the lowest resolutions are L2->SM-bound in conv_umma_kernel: every (tap, 64-channel chunk)
-// stage moves a 16 KB A box AND a 32 KB weight slice for 4 MMAs (512 cycles) -- 94 B/clk against the ~44 B/clk per SM
-// the TMA path delivers with all SMs pulling (ncu: 12.4 TB/s, tensor pipe 50-55 %).  This variant shares each weight
-// slice between TWO M tiles: a stage holds two A boxes and one B slice (64 KB, 3 stages), the two accumulators are the two
-// TMEM halves (2 x 256 columns, so there is no spare accumulator to overlap the epilogue with -- a ~10 % cost against a
-// 1.5x lower L2->SM traffic per MMA).  3x3 / 1x1 stride-1 convs without upsampling only.
-// Measured (micro-batch 256, 512 M tiles = 3.5 per SM): 0.079 vs 0.074 ms per 256->256 layer -- not a win at this tile count;
-// kept behind RFV_FLAG_DUAL for larger micro-batches / resolutions.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int UMMA_DUAL_STAGES = 3;
-constexpr int UMMA_DUAL_STAGE_BYTES = 2 * UMMA_A_BYTES + 256 * 128;
-constexpr int UMMA_DUAL_SMEM_BYTES = UMMA_DUAL_STAGES * UMMA_DUAL_STAGE_BYTES + 1024 + 256;
-
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
-conv_umma_dual_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const ConvParams p,
-                      const UmmaGeom g) {
-    constexpr int BN = 256, B_BYTES = BN * 128;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + UMMA_DUAL_STAGES * UMMA_DUAL_STAGE_BYTES);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + UMMA_DUAL_STAGES;
-    uint64_t* tfull_bar = bars + 2 * UMMA_DUAL_STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&mapA0);
-        tma_prefetch_desc(&mapW);
-        for (int s = 0; s < UMMA_DUAL_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 128); }
-        mbar_fence_init();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int nkb0 = g.taps * g.cch0;
-    const int nkb = nkb0 + g.cch1a + g.cch1b;
-    const int m_pairs = (g.m_tiles + 1) / 2;
-    const int total = m_pairs * g.n_tiles;
-    const int box_shift = g.bw_shift + g.bh_shift;
-    const int tiles_per_img = g.tiles_w * g.tiles_h;
-    auto tile_origin = [&](int mt, int& n0, int& h0, int& w0) {
-        if (box_shift >= 7) {
-            n0 = mt / tiles_per_img;
-            const int r = mt - n0 * tiles_per_img;
-            h0 = (r / g.tiles_w) << g.bh_shift;
-            w0 = (r - (r / g.tiles_w) * g.tiles_w) << g.bw_shift;
-        } else { n0 = mt << (7 - box_shift); h0 = 0; w0 = 0; }
-    };
-    if (warp == 0) {
-        uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
-            int n0[2], h0[2], w0[2];
-            tile_origin(2 * rest, n0[0], h0[0], w0[0]);
-            tile_origin(2 * rest + 1, n0[1], h0[1], w0[1]);   // past the end: the box is zero-filled, the tile never stored
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], UMMA_DUAL_STAGE_BYTES);
-                    uint8_t* st = smem + (size_t)stage * UMMA_DUAL_STAGE_BYTES;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint8_t* sa = st + j * UMMA_A_BYTES;
-                        if (kb < nkb0) {
-                            const int tap = kb / g.cch0, cc = kb - tap * g.cch0;
-                            int dy = 0, dx = 0;
-                            if (g.taps == 9) { dy = tap / 3; dx = tap - dy * 3; dy -= 1; dx -= 1; }
-                            tma_load_4d(sa, &mapA0, &full_bar[stage], cc * 64, w0[j] + dx, h0[j] + dy, n0[j]);
-                        } else {
-                            const int k1 = kb - nkb0;
-                            if (k1 < g.cch1a) tma_load_4d(sa, &mapA1, &full_bar[stage], k1 * 64, w0[j], h0[j], n0[j]);
-                            else tma_load_4d(sa, &mapA2, &full_bar[stage], (k1 - g.cch1a) * 64, w0[j], h0[j], n0[j]);
-                        }
-                    }
-                    tma_load_2d(st + 2 * UMMA_A_BYTES, &mapW, &full_bar[stage], kb * 64, nt * BN);
-                }
-                __syncwarp();
-                if (++stage == UMMA_DUAL_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(UMMA_BM, BN);
-        uint32_t stage = 0, phase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-            mbar_wait(&tempty_bar[0], (it & 1) ^ 1);
-            mbar_wait(&tempty_bar[1], (it & 1) ^ 1);
-            tc_fence_after();
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(smem + (size_t)stage * UMMA_DUAL_STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_sw128(st + 2 * UMMA_A_BYTES);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint64_t adesc = umma_desc_sw128(st + j * UMMA_A_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == nkb - 1) { umma_commit(&tfull_bar[0]); umma_commit(&tfull_bar[1]); }
-                }
-                __syncwarp();
-                if (++stage == UMMA_DUAL_STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp >= 4) {
-        const int q = warp & 3, grp = (warp - 4) >> 2;   // warp-group grp drains the accumulator of the pair's tile grp
-        const int r = q * 32 + lane;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-            const int rest = tile / g.n_tiles, nt = tile - rest * g.n_tiles;
-            const int mt = 2 * rest + grp;
-            int n, h, w;
-            if (box_shift >= 7) {
-                n = mt / tiles_per_img;
-                const int rr = mt - n * tiles_per_img;
-                h = ((rr / g.tiles_w) << g.bh_shift) + (r >> g.bw_shift);
-                w = ((rr - (rr / g.tiles_w) * g.tiles_w) << g.bw_shift) + (r & ((1 << g.bw_shift) - 1));
-            } else {
-                n = (mt << (7 - box_shift)) + (r >> box_shift);
-                h = (r >> g.bw_shift) & ((1 << g.bh_shift) - 1);
-                w = r & ((1 << g.bw_shift) - 1);
-            }
-            const bool valid = n < p.B;
-            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
-            conv_epilogue_tile<BN>(p, taddr, n, valid, valid, pix, nt, lane, &tfull_bar[grp], it & 1, &tempty_bar[grp]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
 }  // namespace rfv

@@ -2,9 +2,11 @@
 //
 // Why: in SS mode an M=128 tcgen05.mma re-reads its 128-row A operand from shared memory in ~82 cycles whatever N is
 // (tools/micro/umma_rate2.cu: N=64 82.8, N=128 81.8, N=192 96, N=256 128 cycles per instruction), so the pixel-major
-// halo kernels (conv_halo.cuh: A = 128 positions, B = C_out weights) cannot exceed 39 % of the tensor pipe on 64-channel
+// formulation (A = 128 positions, B = C_out weights: round 1's conv_halo kernels) cannot exceed 39 % of the tensor pipe on 64-channel
 // layers and 78 % on 128-channel ones.  Here the roles are swapped: A = one 128-row weight block (16 KB, K-major), B = N
-// consecutive positions of the flat padded image (the halo box of conv_halo.cuh, same shifted-start-address trick per tap),
+// consecutive positions of the flat padded image (row pitch W+1: the column shared between rows is zero-filled by the TMA unit, so tap (dy,dx) is the constant row shift
+// dy*(W+1)+dx of ONE shared-memory box per 64-channel chunk -- nine UMMA descriptors over the same bytes; the 128B swizzle is
+// applied on absolute shared-memory address bits, so 128-byte-aligned shifted starts work with base offset 0),
 // N = 192..256, which is the shape the pipe runs at full rate.  The accumulator is D[channel (TMEM lane)][position (column)].
 //
 //   * C_out tile = 128: block rows = output channels, nine taps per 64-channel chunk.
@@ -13,7 +15,7 @@
 //     tap), so the second tap's contribution to position p lands one column to the right: out[p] = top[p] + bot[p+1]; tiles
 //     advance by N-1 positions.  Three pair blocks + three single blocks ((dy,+1), second half zero) per chunk: 6 MMA groups
 //     for 9 taps = 75 % of the pipe (a common column offset admits at most three disjoint pairs in a 3x3 stencil).
-//   * The 1x1 shortcut of a ResidualBlock is extra K chunks at the centre shift (as in conv_halo.cuh); the IDENTITY residual
+//   * The 1x1 shortcut of a ResidualBlock is extra K chunks at the centre shift ; the IDENTITY residual
 //     is one more: a chunk of the residual tensor multiplied by an identity block (exact in fp32 accumulation), so the
 //     epilogue never touches it.  (Tried instead: adding the residual in the epilogue from global memory, 2-byte loads in the
 //     fragment layout -- 0.55 ms on a 64->64 layer issued per half-unit, 0.31 ms with L2 prefetch and loads one half-unit
@@ -24,7 +26,7 @@
 //     (channels are lanes) reduced once per tile; the bf16 result is transposed to [pixel][channel] rows with stmatrix.trans
 //     into a per-warp staging buffer and leaves with 16-byte stores (register mapping verified by tools/micro/frag_test.cu).
 //   * FUSE: GroupNorm(+SiLU) is applied to the segment-0 boxes in shared memory by 8 transform warps between the TMA write
-//     and the MMAs (conv_halo_fused.cuh's scheme; coefficients per (image, channel) from gn_coef_kernel).
+//     and the MMAs (coefficients per (image, channel) from gn_coef_kernel).
 //
 //   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-15  epilogue
 //   (FUSE: warps 16-23 transform)
@@ -66,6 +68,36 @@ constexpr int WA_BLK = 128 * 128;       // one weight block: 128 rows x 64 bf16
 
 __host__ __device__ constexpr int wa_stage_pitch(bool pair) { return pair ? 48 : 80; }   // bytes per staged pixel row (+16 pad)
 __host__ __device__ constexpr int wa_staging_bytes(bool pair) { return WA_EWARPS * 16 * wa_stage_pitch(pair); }   // 16 pixel rows per warp
+
+// scale / shift per (image, channel) of a GroupNorm(8) over a virtual concat of up to two tensors:
+// coef[(n*C + c)*2] = rstd*gamma, coef[..+1] = beta - mean*rstd*gamma
+__global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ stats_a, const float* __restrict__ stats_b,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ coef, int Ca, int Cb, int HW, int slab_shift, float eps) {
+    __shared__ float gmean[8], grstd[8];
+    const int C = Ca + Cb, n = blockIdx.x, cpg = C / 8;
+    if (threadIdx.x < 8) {
+        const int g = threadIdx.x, slab = 1 << slab_shift;
+        float s = 0.f, ss = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; c += slab) {
+            const float* src = (c < Ca) ? stats_a + ((size_t)n * (Ca >> slab_shift) + (c >> slab_shift)) * 2
+                                        : stats_b + ((size_t)n * (Cb >> slab_shift) + ((c - Ca) >> slab_shift)) * 2;
+            s += src[0];
+            ss += src[1];
+        }
+        const float cnt = (float)cpg * (float)HW;
+        const float mean = s / cnt;
+        gmean[g] = mean;
+        grstd[g] = rsqrtf(fmaxf(ss / cnt - mean * mean, 0.f) + eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = grstd[g] * gamma[c];
+        coef[((size_t)n * C + c) * 2] = sc;
+        coef[((size_t)n * C + c) * 2 + 1] = beta[c] - gmean[g] * sc;
+    }
+}
 
 // [Cout][Ktot] K-major bf16 (K = tap*C0 + c | K0 + shortcut c)  ->  [n_tiles][nblk][128 rows][64] blocks in consumption order
 __global__ void pack_wa_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Cout, int C0, int K0, int Ktot, int cch0,

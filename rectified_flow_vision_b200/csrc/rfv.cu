@@ -23,9 +23,6 @@
 #include "common.cuh"
 #include "conv_mma.cuh"
 #include "conv_params.h"
-#include "conv_halo.cuh"
-#include "conv_halo_pair.cuh"
-#include "conv_halo_fused.cuh"
 #include "conv_wa.cuh"
 #include "conv_umma.cuh"
 #include "misc_kernels.cuh"
@@ -148,10 +145,9 @@ struct rfv_engine {
     int cap = 0;       // micro-batch capacity (even)
     int slab_shift = 3;
     int td = 256, sumC = 0;
-    bool keep_acts = false, use_umma = true, use_halo = true, use_pair = true, use_dual = false, use_wa = true;
+    bool keep_acts = false, use_umma = true, use_wa = true;
     int fuse_mode = 1;   // GroupNorm+SiLU inside the consuming conv: 0 never, 1 where measured faster, 2 wherever the kernel applies
     int cluster = 1;  // CTAs per cluster for weight multicast (flags bits 8-10 select 2 or 4; measured slower than 1 on B200)
-    int base_offset_mode = 0;
     EncodeTiledFn encode = nullptr;
 
     std::vector<void*> allocs;
@@ -213,6 +209,12 @@ struct rfv_engine {
     cudaGraphExec_t repack_graph = nullptr;
     cudaStream_t s_bwd = nullptr, s_side = nullptr;
     cudaEvent_t ev_bwd[4]{};
+    // Second sampling lane: batches beyond one micro-batch are integrated as TWO independent chains (this engine and a twin with
+    // its own arena and weight copies) on two streams, enqueued step by step from the calling thread, so one chain's HBM-bound
+    // kernels (GroupNorm apply, thin convs) run under the other chain's tensor-bound convolutions.  Created on first use.
+    rfv_engine* lane = nullptr;
+    bool use_lanes = true;     // RFV_FLAG_ONE_LANE clears it
+    cudaEvent_t ev_fork = nullptr, ev_join[2]{};
     RunCtx fwd_rc;             // rfv_train_forward's context, replayed by rfv_train_backward
     bool have_fwd = false;
     bool two_streams = true;   // RFV_FLAG_ONE_STREAM: run the whole backward pass on one stream (A/B testing)
@@ -230,6 +232,9 @@ struct rfv_engine {
     std::vector<std::string> prof_kinds;
 
     ~rfv_engine() {
+        delete lane;
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto& e : ev_join) if (e) cudaEventDestroy(e);
         for (void* p : allocs) cudaFree(p);
         for (int i = 0; i < 2; ++i) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
@@ -377,17 +382,6 @@ struct rfv_engine {
         if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
         return 0;
     }
-    // output of a halo-reuse conv as {C, H*W pixels, N}: box = 64 channels x `box_pix` consecutive pixels (conv_epilogue_halo)
-    int make_map_pix(CUtensorMap* m, const bf16* base, int C, int HW, int Nd, int box_pix) {
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)Nd};
-        cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)HW * C * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)box_pix, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(RFV_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
-        return 0;
-    }
     int make_map2(CUtensorMap* m, const bf16* base, int K, int rows, int box_rows) {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
         cuuint64_t strides[1] = {(cuuint64_t)K * 2};
@@ -405,52 +399,12 @@ struct rfv_engine {
     // backward writer of acc_of's gradient, i.e. the last forward consumer (decided at run time: consumer counts are
     // final only once the whole plan is built).
     struct FuseReq { const float* coef; int C; int silu; ActP second; };   // GroupNorm applied to segment 0 inside the conv
-    // can this conv take its GroupNorm(+SiLU) inside the kernel?  (halo-reuse geometry, sampling engines only)
+    // can this conv take its GroupNorm(+SiLU) inside the kernel?  (weights-as-A kernel, sampling engines only)
     bool can_fuse_gn(int C0, int Cout, int H, int W) const {
         // fuse_mode 1 (default): only where the halo box is <= 1.5x the tile (32-pixel rows: four rows per tile); 2: everywhere
         const bool here = fuse_mode == 2 || (fuse_mode == 1 && W == 32);
-        return here && !train && use_umma && use_halo && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
+        return here && !train && use_umma && use_wa && H == W && (W == 32 || W == 64 || W == 128) && C0 % 64 == 0 && Cout % 64 == 0;
     }
-    // Geometry and shared-memory plan of a halo-reuse conv (conv_halo.cuh / conv_halo_fused.cuh).  Layers whose weights do
-    // not fit shared memory run DOUBLE tiles (256 positions: every streamed weight block feeds two accumulators).
-    int plan_halo(HaloGeom* gp, int* BNp, size_t* smem, const ConvLayer* L, int W, int H, int bo_mode) {
-        HaloGeom& g = *gp;
-        g.W = W; g.H = H; g.pitch = W + 1;
-        g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
-        const int BN = (L->Cout % 256 == 0) ? 256 : (L->Cout % 128 == 0 ? 128 : 64);
-        *BNp = BN;
-        g.n_tiles = L->Cout / BN;
-        g.base_offset_mode = bo_mode;
-        const int nkb = 9 * g.cch0 + g.cch1a + g.cch1b;
-        const int avail = 227 * 1024 - 2048 - 512 - 8 * HALO_STAGE_BYTES;   // 8 epilogue warps x one 4 KB TMA-store box
-        const int bbytes = BN * 128;
-        auto shape = [&](int sub) {
-            g.sub = sub;
-            g.rows = (g.pitch - 1 + 128 * sub - 1) / g.pitch + 1 + 2;
-            g.tiles_per_img = (g.H * g.pitch + 128 * sub - 1) / (128 * sub);
-            g.a_box_bytes = g.rows * g.pitch * 128;
-            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
-        };
-        shape(1);
-        g.resident_b = (g.n_tiles == 1 && (size_t)nkb * bbytes <= 96 * 1024) ? 1 : 0;
-        if (g.resident_b && (avail - nkb * bbytes) / g.a_stage_bytes < 2) g.resident_b = 0;   // wide images: the boxes need the room
-        int bregion;
-        if (g.resident_b) { g.b_stages = 1; bregion = nkb * bbytes; }
-        else {
-            g.b_stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-            bregion = g.b_stages * bbytes;
-            if (BN <= 128 && !(cfg.flags & RFV_FLAG_NO_DOUBLE_TILE)) {
-                shape(2);
-                if ((avail - 3 * bbytes) / g.a_stage_bytes < 2) shape(1);   // very wide rows: two double-tile boxes do not fit
-            }
-            while (g.b_stages > 3 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * bbytes;
-        }
-        g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
-        if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: halo tile does not fit shared memory", L->name.c_str());
-        *smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 8 * HALO_STAGE_BYTES + 512;
-        return 0;
-    }
-
     // Geometry and shared-memory plan of a weights-as-A conv (conv_wa.cuh).  Picks the tile width N (positions per tile) that
     // wastes the fewest MMA columns among those that keep the whole weight matrix resident; layers that have to stream their
     // weights take the widest tiles (weight blocks are re-fetched per tile).
@@ -563,9 +517,8 @@ struct rfv_engine {
         const bool umma_ok = use_umma && pow2 && (!L->ups || L->subpixel) && L->C0 % 64 == 0 && L->C1a % 64 == 0 &&
                              L->C1b % 64 == 0 && L->Cout % 64 == 0 && gH * gW >= 64 && gW >= 8 && (L->stride == 1 || sc.empty());
         if (L->subpixel && !umma_ok) return fail(RFV_ERR_INVALID, "conv %s: sub-pixel packing needs the tcgen05 path", L->name.c_str());
-        const bool halo_ok = umma_ok && use_halo && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
-                             (out->W == 32 || out->W == 64 || out->W == 128);
-        const bool wa_ok = halo_ok && use_wa && (!resid || resid->C == L->Cout);
+        const bool wa_ok = umma_ok && use_wa && L->ks == 3 && L->stride == 1 && !L->ups && out->W == out->H &&
+                           (out->W == 32 || out->W == 64 || out->W == 128) && (!resid || resid->C == L->Cout);
         if (wa_ok) {
             // weights-as-A kernel (conv_wa.cuh): N = up to 256 positions per MMA, optional in-kernel GroupNorm on segment 0
             struct WBundle { CUtensorMap a0, a0b, a1, a2, r, w; WaGeom g; size_t smem; bool pair, fuse; };
@@ -608,125 +561,9 @@ struct rfv_engine {
                 return cudaGetLastError();
             });
         } else if (fr) {
-            // halo-reuse kernel with GroupNorm(+SiLU) applied to the segment-0 chunks in shared memory (conv_halo_fused.cuh)
-            if (!halo_ok) return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
-            struct FBundle { CUtensorMap a0, a0b, a1, a2, w, o32, o31; HaloGeom g; int BN; size_t smem; };
-            auto bd = std::make_shared<FBundle>();
-            HaloGeom& g = bd->g;
-            g.cch0a = in0->C / 64;
-            RFV_TRY(plan_halo(&g, &bd->BN, &bd->smem, L, out->W, out->H, 0));
-            const int BN = bd->BN;
-            auto amap = [&](CUtensorMap* m, const ActP& t) {
-                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
-            };
-            RFV_TRY(amap(&bd->a0, in0));
-            bd->a0b = bd->a0; bd->a1 = bd->a0; bd->a2 = bd->a0;
-            if (fr->second) RFV_TRY(amap(&bd->a0b, fr->second));
-            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
-            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
-            RFV_TRY(make_map_pix(&bd->o32, out->p, out->C, out->H * out->W, cap, 32));
-            RFV_TRY(make_map_pix(&bd->o31, out->p, out->C, out->H * out->W, cap, 31));
-            p.gn_coef = fr->coef; p.gn_C = fr->C; p.gn_silu = fr->silu;
-            const int sms = num_sms, sumC_ = sumC;
-            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_](const RunCtx& rc, cudaStream_t s) mutable {
-                ConvParams q = p;
-                q.B = rc.B;
-                q.temb_stride = rc.t ? sumC_ : 0;
-                if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
-                HaloGeom g = bd->g;
-                g.m_tiles = rc.B * g.tiles_per_img;
-                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
-                switch (bd->BN) {
-                    case 256: conv_halo_fused_kernel<256><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
-                    case 128: conv_halo_fused_kernel<128><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
-                    default: conv_halo_fused_kernel<64><<<grid, HF_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g);
-                }
-                return cudaGetLastError();
-            });
-        } else if (halo_ok && use_pair && L->Cout % 128 != 0 && (L->C0 >= 128 || L->Cout > 64)) {
-            // 64-output-channel tiles: two taps per MMA (conv_halo_pair.cuh)
-            struct PBundle { CUtensorMap a0, a1, a2, w; HaloGeom g; size_t smem; };
-            auto bd = std::make_shared<PBundle>();
-            HaloGeom& g = bd->g;
-            g.W = out->W; g.H = out->H; g.pitch = g.W + 1;
-            g.rows = (g.pitch - 1 + 127) / g.pitch + 1 + 2;
-            g.tiles_per_img = (g.H * g.pitch + 126) / 127;   // tiles advance by 127 positions
-            g.cch0 = L->C0 / 64; g.cch1a = L->C1a / 64; g.cch1b = L->C1b / 64;
-            g.n_tiles = L->Cout / 64;
-            g.a_box_bytes = g.rows * g.pitch * 128;
-            g.a_stage_bytes = (g.a_box_bytes + 128 + 1023) & ~1023;
-            g.base_offset_mode = 0;
-            const int nblk = 9 * g.cch0 + g.cch1a + g.cch1b;
-            const int avail = 227 * 1024 - 2048 - 512 - HP_XCH_BYTES;
-            g.resident_b = (g.n_tiles == 1 && (size_t)nblk * HP_BLK <= 96 * 1024) ? 1 : 0;
-            int bregion = nblk * HP_BLK;
-            g.b_stages = 1;
-            if (g.resident_b && (avail - bregion) / g.a_stage_bytes < 2) g.resident_b = 0;
-            if (!g.resident_b) {
-                g.b_stages = 3;
-                bregion = g.b_stages * HP_TRI;
-                while (g.b_stages > 2 && (avail - bregion) / g.a_stage_bytes < 2) bregion = --g.b_stages * HP_TRI;
-            }
-            g.a_stages = std::min(4, (avail - bregion) / g.a_stage_bytes);
-            if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: paired halo tile does not fit shared memory", L->name.c_str());
-            bd->smem = 2048 + (size_t)g.a_stages * g.a_stage_bytes + bregion + 256 + HP_XCH_BYTES;
-            auto amap = [&](CUtensorMap* m, const ActP& t) {
-                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
-            };
-            RFV_TRY(amap(&bd->a0, in0));
-            bd->a1 = bd->a0; bd->a2 = bd->a0;
-            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
-            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, 64));
-            const int sms = num_sms, sumC_ = sumC;
-            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
-                ConvParams q = p;
-                q.B = rc.B;
-                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
-                q.temb_stride = rc.t ? sumC_ : 0;
-                if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
-                HaloGeom g = bd->g;
-                g.m_tiles = rc.B * g.tiles_per_img;
-                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
-                conv_halo_pair_kernel<<<grid, HP_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
-                return cudaGetLastError();
-            });
-        } else if (halo_ok) {
-            struct HBundle { CUtensorMap a0, a1, a2, w, o32, o31; HaloGeom g; int BN; size_t smem; };
-            auto bd = std::make_shared<HBundle>();
-            HaloGeom& g = bd->g;
-            RFV_TRY(plan_halo(&g, &bd->BN, &bd->smem, L, out->W, out->H, base_offset_mode));
-            const int BN = bd->BN;
-            auto amap = [&](CUtensorMap* m, const ActP& t) {
-                return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rows, 1);
-            };
-            RFV_TRY(amap(&bd->a0, in0));
-            bd->a1 = bd->a0; bd->a2 = bd->a0;
-            if (sc.size() > 0) RFV_TRY(amap(&bd->a1, sc[0]));
-            if (sc.size() > 1) RFV_TRY(amap(&bd->a2, sc[1]));
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout, BN));
-            RFV_TRY(make_map_pix(&bd->o32, out->p, out->C, out->H * out->W, cap, 32));
-            RFV_TRY(make_map_pix(&bd->o31, out->p, out->C, out->H * out->W, cap, 31));
-            const int sms = num_sms, sumC_ = sumC;
-            push("conv_halo", pre + L->name, fl, [p, bd, sms, sumC_, acc_of, acc_k](const RunCtx& rc, cudaStream_t s) mutable {
-                ConvParams q = p;
-                q.B = rc.B;
-                if (acc_of && acc_k != acc_of->consumers - 1) q.resid = q.out;
-                q.temb_stride = rc.t ? sumC_ : 0;
-                if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
-                HaloGeom g = bd->g;
-                g.m_tiles = rc.B * g.tiles_per_img;
-                const int grid = std::min(g.m_tiles * g.n_tiles, sms);
-                switch (bd->BN) {
-                    case 256: conv_halo_kernel<256><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
-                    case 128: conv_halo_kernel<128><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g); break;
-                    default: conv_halo_kernel<64><<<grid, UMMA_THREADS, bd->smem, s>>>(bd->a0, bd->a1, bd->a2, bd->w, bd->o32, bd->o31, q, g);
-                }
-                return cudaGetLastError();
-            });
+            return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
         } else if (umma_ok) {
-            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; bool dual; };
+            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
             const int bw = std::min(gW, 128), bh = std::min(gH, 128 / bw), bn = 128 / (bw * bh);
@@ -758,7 +595,6 @@ struct rfv_engine {
                                           (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
             }
             g.cluster = cluster;
-            bd->dual = use_dual && BN == 256 && !g.ups && !g.stride2 && cluster == 1;
             RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN / g.cluster));
             bd->max_clusters = num_sms / g.cluster;
             if (g.cluster > 1) {  // how many clusters of this kernel can be co-resident (GPC boundaries strand SMs)
@@ -798,11 +634,6 @@ struct rfv_engine {
                 at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 lc.attrs = at;
                 lc.numAttrs = g.cluster > 1 ? 1 : 0;
-                if (bd->dual) {   // two M tiles per weight slice (conv_umma_dual_kernel)
-                    const int pairs = ((g.m_tiles + 1) / 2) * g.n_tiles;
-                    conv_umma_dual_kernel<<<std::min(pairs, sms), UMMA_THREADS, UMMA_DUAL_SMEM_BYTES, s>>>(bd->a0, bd->a1, bd->a2, bd->w, q, g);
-                    return cudaGetLastError();
-                }
                 switch (bd->BN) {
                     case 256:
                         lc.dynamicSmemBytes = UmmaCfg<256>::SMEM_BYTES;
@@ -1233,18 +1064,10 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU_CHECK(cudaFuncSetAttribute(conv_wa_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_umma_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_DUAL_SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (train) CU_CHECK(cudaFuncSetAttribute(gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 75264));
     td = 4 * mc;
     slab_shift = ilog2(mc / 8);
@@ -1754,9 +1577,6 @@ int rfv_engine::build() {
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_CHECK(cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return 0;
 }
 
@@ -1921,10 +1741,8 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->cap = (cfg->micro_batch + 1) & ~1;
     e->use_umma = !(cfg->flags & RFV_FLAG_NO_UMMA);
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
-    e->use_halo = !(cfg->flags & RFV_FLAG_NO_HALO);
-    e->use_pair = !(cfg->flags & RFV_FLAG_NO_PAIR);
     e->use_wa = !(cfg->flags & RFV_FLAG_NO_WA);
-    e->use_dual = (cfg->flags & RFV_FLAG_DUAL) != 0;
+    e->use_lanes = !(cfg->flags & RFV_FLAG_ONE_LANE) && !(cfg->flags & RFV_FLAG_TRAIN);
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
     e->fuse_mode = (cfg->flags & RFV_FLAG_FUSE_GN) ? 2 : ((cfg->flags & RFV_FLAG_NO_FUSE_GN) ? 0 : 1);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
@@ -1936,6 +1754,8 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     }
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_weights, cudaEventDisableTiming));
     CU_CHECK(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    for (auto& ev : e->ev_join) CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -1995,6 +1815,7 @@ RFV_EXPORT int rfv_set_tensor(rfv_handle h, const char* name, const float* dev_p
         if (ce != cudaSuccess) rc = fail(RFV_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(ce));
     }
     const int rl = h->leave(s);   // also on failure: whatever was enqueued must order later calls
+    if (rc == 0 && rl == 0 && h->lane) return rfv_set_tensor(h->lane, name, dev_ptr, numel, stream);
     return rc ? rc : rl;
 }
 
@@ -2056,27 +1877,110 @@ RFV_EXPORT int rfv_velocity(rfv_handle h, const float* x, const float* t, float*
     return h->leave((cudaStream_t)stream);
 }
 
-static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj, int save_every, size_t traj_stride,
-                       const float* tx0, const float* tx1, float* mse, cudaStream_t s) {
-    const double dt = 1.0 / num_steps;  // Python double, like models/base_flow.py:158
+// One micro-batch's Euler loop as a resumable sequence, so that two lanes can be enqueued alternately from one thread.
+struct EulerRun {
+    rfv_engine* e = nullptr;
+    cudaStream_t s = nullptr;
+    float* x = nullptr;
+    int B = 0, num_steps = 0;
+    float* traj = nullptr;
+    int save_every = 0;
+    size_t traj_stride = 0;
+    const float *tx0 = nullptr, *tx1 = nullptr;
+    float* mse = nullptr;
+    int i = 0;
+    bool table = false;
+};
+
+static int euler_begin(EulerRun& r) {
+    rfv_engine* h = r.e;
+    const double dt = 1.0 / r.num_steps;  // Python double, like models/base_flow.py:158
     // every step's time is known now: one batched time-MLP + block-projection launch fills rows 0 .. num_steps-1 of the
     // projection table instead of two latency-bound single-row launches per step (0.07 ms of a 4.7 ms step at 256 images)
-    const bool table = num_steps > 1 && num_steps <= h->cap && !(h->cfg.flags & RFV_FLAG_TEMB_PER_STEP);
-    if (table) {
-        fill_step_times_kernel<<<(num_steps + 255) / 256, 256, 0, s>>>(h->t_steps, num_steps, dt);
+    r.table = r.num_steps > 1 && r.num_steps <= h->cap && !(h->cfg.flags & RFV_FLAG_TEMB_PER_STEP);
+    r.i = 0;
+    if (r.table) {
+        fill_step_times_kernel<<<(r.num_steps + 255) / 256, 256, 0, r.s>>>(h->t_steps, r.num_steps, dt);
         CU_CHECK(cudaGetLastError());
         RunCtx rt;
-        rt.B = num_steps; rt.t = h->t_steps; rt.temb_only = true;
-        RFV_TRY(h->run_forward(rt, s));
+        rt.B = r.num_steps; rt.t = h->t_steps; rt.temb_only = true;
+        RFV_TRY(h->run_forward(rt, r.s));
     }
-    for (int i = 0; i < num_steps; ++i) {
-        RunCtx rc;
-        rc.B = B; rc.x = x; rc.out = x; rc.mode = 1;
-        rc.t = nullptr; rc.t_scalar = (float)(i * dt); rc.dt = (float)dt;
-        if (table) rc.temb_row = i;
-        if (traj && save_every > 0 && (i + 1) % save_every == 0) rc.traj = traj + (size_t)((i + 1) / save_every - 1) * traj_stride;
-        if (mse) { rc.tgt_x0 = tx0; rc.tgt_x1 = tx1; rc.mse = mse + i; }
-        RFV_TRY(h->run_forward(rc, s));
+    return 0;
+}
+
+static int euler_step(EulerRun& r) {
+    const double dt = 1.0 / r.num_steps;
+    const int i = r.i++;
+    RunCtx rc;
+    rc.B = r.B; rc.x = r.x; rc.out = r.x; rc.mode = 1;
+    rc.t = nullptr; rc.t_scalar = (float)(i * dt); rc.dt = (float)dt;
+    if (r.table) rc.temb_row = i;
+    if (r.traj && r.save_every > 0 && (i + 1) % r.save_every == 0) rc.traj = r.traj + (size_t)((i + 1) / r.save_every - 1) * r.traj_stride;
+    if (r.mse) { rc.tgt_x0 = r.tx0; rc.tgt_x1 = r.tx1; rc.mse = r.mse + i; }
+    return r.e->run_forward(rc, r.s);
+}
+
+static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj, int save_every, size_t traj_stride,
+                       const float* tx0, const float* tx1, float* mse, cudaStream_t s) {
+    EulerRun r;
+    r.e = h; r.s = s; r.x = x; r.B = B; r.num_steps = num_steps; r.traj = traj; r.save_every = save_every;
+    r.traj_stride = traj_stride; r.tx0 = tx0; r.tx1 = tx1; r.mse = mse;
+    RFV_TRY(euler_begin(r));
+    while (r.i < num_steps) RFV_TRY(euler_step(r));
+    return 0;
+}
+
+// the twin engine of the second lane: same configuration, weights copied device-to-device from this engine's fp32 masters
+static int ensure_lane(rfv_handle h, cudaStream_t s) {
+    if (h->lane) return 0;
+    rfv_handle twin = nullptr;
+    rfv_config cfg = h->cfg;
+    cfg.flags |= RFV_FLAG_ONE_LANE;   // lanes do not nest
+    RFV_TRY(rfv_create(&cfg, &twin));
+    for (size_t i = 0; i < h->params.size(); ++i) {
+        const Param& p = h->params[i];
+        if (!p.loaded) continue;
+        const int rc = rfv_set_tensor(twin, p.name.c_str(), p.f32, p.numel, s);
+        if (rc) { rfv_destroy(twin); return rc; }
+    }
+    twin->profiling = false;
+    h->lane = twin;
+    return 0;
+}
+
+// Rows [0, n) in micro-batches, the first half of the chunks on lane 0 (this engine), the rest on lane 1 (the twin); the two
+// chains advance one Euler step at a time, alternately, so both streams always hold queued work.  `begin(lane, engine, chunk
+// index within the lane, first row, rows)` returns the device state buffer of the chunk (after any H2D copy it enqueues on the
+// way); `end` is called when the chunk's last step is enqueued.
+template <typename Begin, typename End>
+static int run_two_lanes(rfv_handle h, int64_t n, int num_steps, cudaStream_t s0, cudaStream_t s1, Begin begin, End end) {
+    const int64_t chunks = (n + h->cap - 1) / h->cap, half = (chunks + 1) / 2;
+    struct Lane { rfv_engine* e; cudaStream_t s; int64_t c, c_end, k; bool open; EulerRun run; } ln[2] = {
+        {h, s0, 0, half, 0, false, {}}, {h->lane, s1, half, chunks, 0, false, {}}};
+    for (;;) {
+        bool any = false;
+        for (auto& l : ln) {
+            if (l.c >= l.c_end) continue;
+            any = true;
+            if (!l.open) {
+                const int64_t b0 = l.c * h->cap;
+                const int B = (int)std::min<int64_t>(h->cap, n - b0);
+                float* x = nullptr;
+                RFV_TRY(begin((int)(&l - ln), l.e, l.k, b0, B, &x));
+                l.run = EulerRun{};
+                l.run.e = l.e; l.run.s = l.s; l.run.x = x; l.run.B = B; l.run.num_steps = num_steps;
+                RFV_TRY(euler_begin(l.run));
+                l.open = true;
+            }
+            RFV_TRY(euler_step(l.run));
+            if (l.run.i >= num_steps) {
+                RFV_TRY(end((int)(&l - ln), l.e, l.k, l.c * h->cap, l.run.B));
+                l.open = false;
+                ++l.c; ++l.k;
+            }
+        }
+        if (!any) break;
     }
     return 0;
 }
@@ -2084,13 +1988,31 @@ static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj
 RFV_EXPORT int rfv_euler_sample(rfv_handle h, float* x, int64_t batch, int num_steps, float* traj, int save_every, void* stream) {
     if (!h || !x || batch < 1 || num_steps < 1) return fail(RFV_ERR_INVALID, "bad argument");
     const size_t ie = image_elems(h);
-    RFV_TRY(h->enter((cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    RFV_TRY(h->enter(s));
+    if (batch > h->cap && !traj && h->use_lanes && !h->profiling) {
+        RFV_TRY(ensure_lane(h, s));
+        // fork: both lane streams start after everything enqueued on the caller's stream (incl. weight uploads) ...
+        CU_CHECK(cudaEventRecord(h->ev_fork, s));
+        CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_fork, 0));
+        CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->ev_fork, 0));
+        CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->lane->ev_weights, 0));
+        RFV_TRY(run_two_lanes(h, batch, num_steps, h->s_cmp, h->lane->s_cmp,
+            [&](int, rfv_engine*, int64_t, int64_t b0, int, float** xo) { *xo = x + b0 * ie; return 0; },
+            [&](int, rfv_engine*, int64_t, int64_t, int) { return 0; }));
+        // ... join: the caller's stream continues when both chains are done
+        CU_CHECK(cudaEventRecord(h->ev_join[0], h->s_cmp));
+        CU_CHECK(cudaEventRecord(h->ev_join[1], h->lane->s_cmp));
+        CU_CHECK(cudaStreamWaitEvent(s, h->ev_join[0], 0));
+        CU_CHECK(cudaStreamWaitEvent(s, h->ev_join[1], 0));
+        return h->leave(s);
+    }
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
         const int B = (int)std::min<int64_t>(h->cap, batch - b0);
         RFV_TRY(euler_chunk(h, x + b0 * ie, B, num_steps, traj ? traj + b0 * ie : nullptr, save_every, (size_t)batch * ie, nullptr,
-                            nullptr, nullptr, (cudaStream_t)stream));
+                            nullptr, nullptr, s));
     }
-    return h->leave((cudaStream_t)stream);
+    return h->leave(s);
 }
 
 RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, float* out_host, int64_t n, int num_steps) {
@@ -2098,20 +2020,43 @@ RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, floa
     const size_t ie = image_elems(h);
     CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_weights, 0));  // uploads were enqueued on the caller's stream
     RFV_TRY(h->enter(h->s_cmp));
-    int64_t idx = 0;
-    for (int64_t b0 = 0; b0 < n; b0 += h->cap, ++idx) {
-        const int B = (int)std::min<int64_t>(h->cap, n - b0);
-        const int k = (int)(idx & 1);
-        // buffer k is free once its previous result has left the device
-        if (idx >= 2) CU_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[k], 0));
-        CU_CHECK(cudaMemcpyAsync(h->xbuf[k], noise_host + b0 * ie, (size_t)B * ie * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
-        CU_CHECK(cudaEventRecord(h->ev_in[k], h->s_h2d));
-        CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
-        RFV_TRY(euler_chunk(h, h->xbuf[k], B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
-        CU_CHECK(cudaEventRecord(h->ev_done[k], h->s_cmp));
-        CU_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[k], 0));
-        CU_CHECK(cudaMemcpyAsync(out_host + b0 * ie, h->xbuf[k], (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
-        CU_CHECK(cudaEventRecord(h->ev_out[k], h->s_d2h));
+    // per chunk: H2D on the engine's copy-in stream -> Euler loop on its compute stream -> D2H on its copy-out stream, double
+    // buffered (buffer k is free once its previous result has left the device)
+    auto begin = [&](int, rfv_engine* e, int64_t k, int64_t b0, int B, float** xo) {
+        const int kb = (int)(k & 1);
+        if (k >= 2) CU_CHECK(cudaStreamWaitEvent(e->s_h2d, e->ev_out[kb], 0));
+        CU_CHECK(cudaMemcpyAsync(e->xbuf[kb], noise_host + b0 * ie, (size_t)B * ie * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
+        CU_CHECK(cudaEventRecord(e->ev_in[kb], e->s_h2d));
+        CU_CHECK(cudaStreamWaitEvent(e->s_cmp, e->ev_in[kb], 0));
+        *xo = e->xbuf[kb];
+        return 0;
+    };
+    auto end = [&](int, rfv_engine* e, int64_t k, int64_t b0, int B) {
+        const int kb = (int)(k & 1);
+        CU_CHECK(cudaEventRecord(e->ev_done[kb], e->s_cmp));
+        CU_CHECK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[kb], 0));
+        CU_CHECK(cudaMemcpyAsync(out_host + b0 * ie, e->xbuf[kb], (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        CU_CHECK(cudaEventRecord(e->ev_out[kb], e->s_d2h));
+        return 0;
+    };
+    const bool lanes = n > h->cap && h->use_lanes && !h->profiling;
+    if (lanes) {
+        RFV_TRY(ensure_lane(h, h->s_cmp));
+        CU_CHECK(cudaEventRecord(h->ev_fork, h->s_cmp));
+        CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->ev_fork, 0));   // a new twin's weights were written on this stream,
+        CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->lane->ev_weights, 0));   // later uploads on the caller's
+        RFV_TRY(run_two_lanes(h, n, num_steps, h->s_cmp, h->lane->s_cmp, begin, end));
+        CU_CHECK(cudaStreamSynchronize(h->lane->s_d2h));
+        CU_CHECK(cudaStreamSynchronize(h->lane->s_cmp));
+    } else {
+        int64_t k = 0;
+        for (int64_t b0 = 0; b0 < n; b0 += h->cap, ++k) {
+            const int B = (int)std::min<int64_t>(h->cap, n - b0);
+            float* xd = nullptr;
+            RFV_TRY(begin(0, h, k, b0, B, &xd));
+            RFV_TRY(euler_chunk(h, xd, B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
+            RFV_TRY(end(0, h, k, b0, B));
+        }
     }
     CU_CHECK(cudaStreamSynchronize(h->s_d2h));
     CU_CHECK(cudaStreamSynchronize(h->s_cmp));
@@ -2317,8 +2262,12 @@ RFV_EXPORT int rfv_optimizer_step(rfv_handle h, const rfv_adamw* hp, float* grad
 
 RFV_EXPORT int64_t rfv_launch_count(rfv_handle h, int reset) {
     if (!h) return 0;
-    const int64_t v = h->launches;
+    int64_t v = h->launches;
     if (reset) h->launches = 0;
+    if (h->lane) {
+        v += h->lane->launches;
+        if (reset) h->lane->launches = 0;
+    }
     return v;
 }
 

@@ -6,7 +6,7 @@
 // NHWC tensor {64 channels, pitch, rows} lands in shared memory as 128-byte rows (one pixel's 64 channels) in 8-row
 // 128B-swizzle atoms -- exactly the canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
 // units: SBO = 1024 B between 8-pixel groups, LBO = distance between 64-channel blocks of the M (or N) dimension.
-//   * B operand (N = 64 output channels): the dY tile, R whole image rows in the flat padded space of conv_halo.cuh
+//   * B operand (N = 64 output channels): the dY tile, R whole image rows in the flat padded space of conv_wa.cuh
 //     (row pitch W+1, position 0 of each row is a zero column supplied by the TMA unit's out-of-bounds fill).
 //   * A operand (M = 128): TWO taps of the input halo box {64 ch, W+1, R+2 rows}.  In the padded space tap (dy,dx) is
 //     the constant row shift (1+dy)*(W+1)+dx of the box, so "the same 64 channels one tap further" is simply another

@@ -39,16 +39,33 @@ def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, 
     if not gather:
         return local
     backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    width = -(-rows.shape[0] // world)  # equal-sized slots for the collective; short shards are padded
-    slot = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
-    slot[: hi - lo].copy_(local, non_blocking=True)
-    gathered = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered, slot, group=group)
-    gathered = gathered.cpu()
+    n = rows.shape[0]
+    width = -(-n // world)  # equal-sized slots for the collective; short shards are padded
+    shape = tuple(local.shape[1:])
+    if backend == "nccl":
+        # device all-gather over NVLink, then ONE device->host copy into a pinned buffer (a pageable .cpu() of the gathered
+        # tensor runs at a few GB/s and would cost more than the collective)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        gathered_dev = torch.empty((world * width,) + shape, dtype=local.dtype, device=dev)
+        slot = gathered_dev[rank * width:(rank + 1) * width]      # gather in place: this rank's slot is its own input
+        slot[: hi - lo].copy_(local, non_blocking=True)
+        if hi - lo < width:
+            slot[hi - lo:].zero_()
+        dist.all_gather_into_tensor(gathered_dev, slot, group=group)
+        gathered = torch.empty(gathered_dev.shape, dtype=local.dtype, pin_memory=True)
+        gathered.copy_(gathered_dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        del gathered_dev
+    else:
+        slot = torch.zeros((width,) + shape, dtype=local.dtype)
+        slot[: hi - lo].copy_(local)
+        gathered = torch.empty((world * width,) + shape, dtype=local.dtype)
+        dist.all_gather_into_tensor(gathered, slot, group=group)
+    if width * world == n:
+        return gathered           # equal shards: the slots already are the rows in order
     parts = []
     for r in range(world):
-        a, b = shard_bounds(rows.shape[0], r, world)
+        a, b = shard_bounds(n, r, world)
         parts.append(gathered[r * width: r * width + (b - a)])
     return torch.cat(parts, dim=0)
 

@@ -17,6 +17,7 @@ from . import _build
 
 RFV_MAX_LEVELS = 8
 FLAG_NO_UMMA = 1
+FLAG_ONE_LANE = 2
 FLAG_KEEP_ACTS = 4
 FLAG_TRAIN = 32
 
@@ -149,6 +150,8 @@ class Engine:
         cfg.micro_batch = micro_batch or default_micro_batch(image_size)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         cfg.flags = int(os.environ.get("RFV_FLAGS", "0")) if flags is None else flags
+        if os.environ.get("RFV_LANES", "2") == "1":
+            cfg.flags |= FLAG_ONE_LANE      # A/B: one chain of micro-batches instead of two alternately enqueued ones
         if train:
             cfg.flags |= FLAG_TRAIN
         self.train = bool(cfg.flags & FLAG_TRAIN)
@@ -157,12 +160,7 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(self.lib.rfv_create(C.byref(cfg), C.byref(h)))
         self.h = h
-        # Second native handle ("lane") for sampling: two independent micro-batch chains on two streams let the GPU run
-        # one chain's HBM-bound kernels (GroupNorm apply, thin convs) under the other chain's tensor-bound convolutions.
-        self.h2 = None
         self._cfg = cfg
-        self._lane_streams = None
-        self._pool = None
         self._versions: Dict[str, tuple] = {}
         self.tensor_names = []
         buf = C.create_string_buffer(256)
@@ -173,40 +171,11 @@ class Engine:
 
     def __del__(self):
         try:
-            if getattr(self, "_pool", None):
-                self._pool.shutdown(wait=True)
-            for name in ("h2", "h"):
-                if getattr(self, name, None):
-                    self.lib.rfv_destroy(getattr(self, name))
-                    setattr(self, name, None)
+            if getattr(self, "h", None):
+                self.lib.rfv_destroy(self.h)
+                self.h = None
         except Exception:
             pass
-
-    # ----- second lane -----------------------------------------------------------------------------------
-    def _ensure_second_lane(self):
-        if self.h2 is not None or self.train or os.environ.get("RFV_LANES", "2") == "1":
-            return self.h2 is not None
-        h = _VP()
-        with torch.cuda.device(self.device):
-            _check(self.lib.rfv_create(C.byref(self._cfg), C.byref(h)))
-            self.h2 = h
-            for full, numel in self.tensor_names:          # same weights: device-to-device from lane 0's fp32 copies
-                tmp = torch.empty(numel, dtype=torch.float32, device=self.device)
-                _check(self.lib.rfv_get_master(self.h, full.encode(), tmp.data_ptr(), numel, self._stream()))
-                _check(self.lib.rfv_set_tensor(self.h2, full.encode(), tmp.data_ptr(), numel, self._stream()))
-            self._lane_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
-        import concurrent.futures
-        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=2)
-        return True
-
-    def _split(self, n: int):
-        """Rows of lane 0 / lane 1: halves rounded to the micro-batch (0 for lane 1 when the batch is a single chunk)."""
-        mb = self.micro_batch
-        if n <= mb:
-            return n, 0
-        chunks = -(-n // mb)
-        n0 = min(n, ((chunks + 1) // 2) * mb)
-        return n0, n - n0
 
     # ----- helpers ---------------------------------------------------------------------------------------
     def _stream(self):
@@ -253,8 +222,6 @@ class Engine:
                 if src.numel() != numel:
                     raise ValueError(f"{full}: expected {numel} elements, got {src.numel()}")
                 _check(self.lib.rfv_set_tensor(self.h, full.encode(), src.data_ptr(), numel, self._stream()))
-                if self.h2 is not None:
-                    _check(self.lib.rfv_set_tensor(self.h2, full.encode(), src.data_ptr(), numel, self._stream()))
                 self._versions[full] = tag
                 del src
 
@@ -283,36 +250,10 @@ class Engine:
         if save_every and save_every > 0 and num_steps // save_every > 0:
             traj = torch.empty((num_steps // save_every,) + tuple(x.shape), dtype=torch.float32, device=x.device)
             tp = traj.data_ptr()
-        n0, n1 = self._split(x.shape[0])
-        if tp is not None or n1 == 0 or not self._ensure_second_lane():
-            with torch.cuda.device(self.device):
-                _check(self.lib.rfv_euler_sample(self.h, x.data_ptr(), x.shape[0], int(num_steps), tp,
-                                                 int(save_every or 0), self._stream()))
-            return x, traj
-        # two lanes: rows [0, n0) on handle 0 / stream 0, rows [n0, n) on handle 1 / stream 1, enqueued by two host threads
-        # (one thread would fill its stream's launch queue and start the second chain only when the first is nearly done)
-        cur = torch.cuda.current_stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        row = x[0].numel() * 4
-
-        def run(k, handle, off, cnt):
-            with torch.cuda.device(self.device):
-                st = self._lane_streams[k]
-                st.wait_event(ready)
-                rc = self.lib.rfv_euler_sample(handle, C.c_void_p(x.data_ptr() + off * row), cnt, int(num_steps), None, 0,
-                                               C.c_void_p(st.cuda_stream))
-                msg = self.lib.rfv_last_error() if rc != 0 else None   # thread-local in the library: read it here
-                ev = torch.cuda.Event()
-                ev.record(st)
-                return rc, msg, ev
-
-        futs = [self._pool.submit(run, 0, self.h, 0, n0), self._pool.submit(run, 1, self.h2, n0, n1)]
-        for f in futs:
-            rc, msg, ev = f.result()
-            if rc != 0:
-                raise RfvError(f"rfv error {rc}: {msg.decode() if msg else '?'}")
-            cur.wait_event(ev)
+        # batches beyond one micro-batch run as two alternately enqueued chains on two streams INSIDE the library
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_euler_sample(self.h, x.data_ptr(), x.shape[0], int(num_steps), tp,
+                                             int(save_every or 0), self._stream()))
         return x, traj
 
     def euler_sample_host(self, noise_host: torch.Tensor, num_steps: int, out: Optional[torch.Tensor] = None):
@@ -330,26 +271,10 @@ class Engine:
             raise ValueError("out must be a contiguous CPU fp32 tensor of the noise's shape")
         if out is None:
             out = torch.empty_like(noise_host, pin_memory=noise_host.is_pinned())
-        n = noise_host.shape[0]
-        n0, n1 = self._split(n)
-        if n1 == 0 or not self._ensure_second_lane():
-            with torch.cuda.device(self.device):
-                _check(self.lib.rfv_euler_sample_host(self.h, noise_host.data_ptr(), out.data_ptr(), n, int(num_steps)))
-            return out
         torch.cuda.current_stream(self.device).synchronize()   # weight uploads were enqueued on the caller's stream
-        row = noise_host[0].numel() * 4
-
-        def run(handle, off, cnt):
-            with torch.cuda.device(self.device):
-                rc = self.lib.rfv_euler_sample_host(handle, C.c_void_p(noise_host.data_ptr() + off * row),
-                                                    C.c_void_p(out.data_ptr() + off * row), cnt, int(num_steps))
-                return rc, (self.lib.rfv_last_error() if rc != 0 else None)
-
-        futs = [self._pool.submit(run, self.h, 0, n0), self._pool.submit(run, self.h2, n0, n1)]
-        for f in futs:
-            rc, msg = f.result()
-            if rc != 0:
-                raise RfvError(f"rfv error {rc}: {msg.decode() if msg else '?'}")
+        with torch.cuda.device(self.device):
+            _check(self.lib.rfv_euler_sample_host(self.h, noise_host.data_ptr(), out.data_ptr(), noise_host.shape[0],
+                                                  int(num_steps)))
         return out
 
     def straightness(self, x0: torch.Tensor, x1: torch.Tensor, num_points: int) -> torch.Tensor:
@@ -480,10 +405,7 @@ class Engine:
 
     # ----- introspection ---------------------------------------------------------------------------------
     def launch_count(self, reset: bool = False) -> int:
-        n = int(self.lib.rfv_launch_count(self.h, 1 if reset else 0))
-        if self.h2 is not None:
-            n += int(self.lib.rfv_launch_count(self.h2, 1 if reset else 0))
-        return n
+        return int(self.lib.rfv_launch_count(self.h, 1 if reset else 0))   # both lanes
 
     def flops_per_image(self) -> float:
         return float(self.lib.rfv_flops_per_image(self.h))

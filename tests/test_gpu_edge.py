@@ -82,34 +82,48 @@ def test_pair_generation_full_job_shard_is_deterministic():
     assert torch.equal(a0, torch.randn(40, 3, 32, 32, generator=torch.Generator().manual_seed(42)))
 
 
-def test_two_lane_sampling_matches_single_lane(monkeypatch):
-    """Batches larger than one micro-batch are split over two native handles / streams / host threads; rows are
-    independent, so the result must not depend on the split (RFV_LANES=1 forces the single-lane path)."""
+def test_two_lane_sampling_matches_single_lane():
+    """Batches larger than one micro-batch are integrated INSIDE the library as two alternately enqueued chains (the engine
+    and a twin with its own arena) on two streams; rows are independent, so the result must not depend on the split
+    (RFV_FLAG_ONE_LANE forces one chain).  The C-ABI caller gets the two lanes too: nothing here is scheduled from Python."""
     from rectified_flow_vision_b200 import engine as E
     m = _model()
-    x = torch.randn(20, 3, 32, 32, generator=torch.Generator().manual_seed(21)).cuda()
+    x = torch.randn(21, 3, 32, 32, generator=torch.Generator().manual_seed(21)).cuda()     # 6 chunks: 4+4+4 | 4+4+1
     two = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=4)
     two.sync_weights(m.velocity_net)
+    two.launch_count(reset=True)
     a, _ = two.euler_sample(x, 3)
-    assert two.h2 is not None                                   # the second lane was created and used
-    monkeypatch.setenv("RFV_LANES", "1")
-    one = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=4)
+    n_two = two.launch_count(reset=True)
+    one = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=4, flags=E.FLAG_ONE_LANE)
     one.sync_weights(m.velocity_net)
+    one.launch_count(reset=True)
     b, _ = one.euler_sample(x, 3)
-    assert one.h2 is None
+    assert n_two == one.launch_count(reset=True) > 0            # the twin's launches are counted
     assert util.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-2
     host = x.cpu().pin_memory()
     ha = two.euler_sample_host(host, 3)
-    assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2
+    hb = one.euler_sample_host(host, 3)
+    assert util.rel_l2(ha.numpy(), a.cpu().numpy()) < 2e-2 and util.rel_l2(hb.numpy(), a.cpu().numpy()) < 2e-2
+    # weights uploaded AFTER the twin exists reach both lanes: rows of lane 1 must follow the new weights as well
+    with torch.no_grad():
+        for p in m.velocity_net.parameters():
+            p.mul_(0.9)
+    two.sync_weights(m.velocity_net)
+    one.sync_weights(m.velocity_net)
+    a2, _ = two.euler_sample(x, 3)
+    b2, _ = one.euler_sample(x, 3)
+    assert util.rel_l2(a2.cpu().numpy(), b2.cpu().numpy()) < 2e-2
+    assert util.rel_l2(a2[16:].cpu().numpy(), a[16:].cpu().numpy()) > 1e-2
 
 
-NO_WA = 1048576   # RFV_FLAG_NO_WA: pixel-major halo kernels instead of the weights-as-A kernel
+NO_WA = 1048576   # RFV_FLAG_NO_WA: per-tap implicit-GEMM kernel instead of the weights-as-A kernel
 
 
-@pytest.mark.parametrize("flag,name", [(NO_WA, "pixel-major halo kernels (no weights-as-A)"), (NO_WA | 16, "128-position tiles (no double tiles)"), (128, "dual M tiles"),
-                                       (4096, "GroupNorm fused into every weights-as-A conv"), (NO_WA | 4096, "GroupNorm fused into every halo conv"), (NO_WA | 64, "no tap pairing"), (8, "no halo reuse"),
-                                       (512, "cluster-2 weight multicast"), (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"), (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"),
-                                       (524288, "no GroupNorm fusion")])
+@pytest.mark.parametrize("flag,name", [(NO_WA, "per-tap implicit-GEMM kernel everywhere (no weights-as-A)"),
+                                       (4096, "GroupNorm fused into every weights-as-A conv"), (512, "cluster-2 weight multicast"),
+                                       (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"),
+                                       (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"), (524288, "no GroupNorm fusion"),
+                                       (1, "mma.sync implicit-GEMM convs (no tcgen05)")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
     """The A/B kernels kept behind RFV_FLAG_* (include/rfv.h) compute the same velocity as the default plan."""
     from rectified_flow_vision_b200 import engine as E

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_REF_L2, TOL_REF_MAX, TOL_POLICY_L2, MIN_PSNR = 3e-2, 5e-2, 2e-2, 45.0
 TOL_LOSS, TOL_GNORM, TOL_GRAD_L2 = 5e-3, 1e-2, 5e-2
-FLAG_KEEP_ACTS, FLAG_FUSE_GN, FLAG_NO_FUSE_GN, FLAG_NO_HALO, FLAG_NO_UMMA = 4, 4096, 524288, 8, 1
+FLAG_KEEP_ACTS, FLAG_FUSE_GN, FLAG_NO_FUSE_GN, FLAG_NO_WA, FLAG_NO_UMMA = 4, 4096, 524288, 1048576, 1
 
 
 @pytest.fixture(scope="module", params=["pert_small32", "pert_default64", "pert_default128"])
@@ -52,8 +52,8 @@ def test_velocity_on_perturbed_weights(case):
     assert l2 <= TOL_REF_L2 and mx <= TOL_REF_MAX
 
 
-@pytest.mark.parametrize("flags,name", [(0, "default plan"), (FLAG_FUSE_GN, "GroupNorm fused into every halo conv"),
-                                        (FLAG_NO_FUSE_GN, "GroupNorm never fused"), (FLAG_NO_HALO, "per-tap tcgen05 kernel"),
+@pytest.mark.parametrize("flags,name", [(0, "default plan"), (FLAG_FUSE_GN, "GroupNorm fused into every weights-as-A conv"),
+                                        (FLAG_NO_FUSE_GN, "GroupNorm never fused"), (FLAG_NO_WA, "per-tap tcgen05 kernel"),
                                         (FLAG_NO_UMMA, "mma.sync kernels")])
 def test_every_kernel_plan_on_perturbed_weights(flags, name):
     """gamma / beta indexing of each GroupNorm code path (stand-alone apply, coefficient table of the fused conv, virtual
