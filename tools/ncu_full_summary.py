@@ -33,7 +33,7 @@ UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msec
 
 
 def klass(name: str) -> str:
-    for k in ("conv_wa", "conv_umma", "conv_mma", "gn_apply", "gn_coef", "input_conv", "output_conv", "attn", "temb"):
+    for k in ("input_conv", "output_conv", "conv_wa", "conv_umma", "conv_mma", "gn_apply", "gn_coef", "attn", "temb"):
         if k in name:
             return "attention" if k == "attn" else k
     return "other"
