@@ -28,8 +28,8 @@
 //   * FUSE: GroupNorm(+SiLU) is applied to the segment-0 boxes in shared memory by 8 transform warps between the TMA write
 //     and the MMAs (coefficients per (image, channel) from gn_coef_kernel).
 //
-//   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-15  epilogue
-//   (FUSE: warps 16-23 transform)
+//   warp 0  box producer   warp 1  MMA issuer   warp 2  TMEM allocator   warp 3  weight producer   warps 4-19  epilogue
+//   (FUSE: warps 4-15 epilogue, warps 16-23 transform)
 // Replaces nn.Conv2d call sites models/unet.py:38,41(+51) at the 64x64 / 32x32 (/128x128) levels, and their data gradients.
 #pragma once
 #include <cuda.h>
@@ -60,14 +60,17 @@ struct WaGeom {
                                   // 8 = no TMA loads (barriers only)
 };
 
-constexpr int WA_EWARPS = 12;                              // epilogue warps (three per TMEM lane quarter)
-constexpr int WA_THREADS = (4 + WA_EWARPS) * 32;           // 4 control + 12 epilogue warps
+// Epilogue warps: four per TMEM lane quarter (16 half-units of an N = 256 tile split evenly, four each), three in the FUSE
+// kernels whose register file also has to hold the transform warps.  ncu (r2f, 64->64 PAIR layer, 12 warps): 780 instructions
+// per warp and tile at an IPC of 0.18 per warp -- the warps are bound by their own dependent-issue latency, not by the
+// schedulers (issue slots 56 % busy), so more warps with less work each is what shortens the per-tile epilogue.
+__host__ __device__ constexpr int wa_ewarps(bool fuse) { return fuse ? 12 : 16; }
 constexpr int WA_TWARPS = 8;                               // transform warps (FUSE)
-constexpr int WA_FUSE_THREADS = WA_THREADS + WA_TWARPS * 32;
+__host__ __device__ constexpr int wa_threads(bool fuse) { return (4 + wa_ewarps(fuse) + (fuse ? WA_TWARPS : 0)) * 32; }
 constexpr int WA_BLK = 128 * 128;       // one weight block: 128 rows x 64 bf16
 
 __host__ __device__ constexpr int wa_stage_pitch(bool pair) { return pair ? 48 : 80; }   // bytes per staged pixel row (+16 pad)
-__host__ __device__ constexpr int wa_staging_bytes(bool pair) { return WA_EWARPS * 16 * wa_stage_pitch(pair); }   // 16 pixel rows per warp
+__host__ __device__ constexpr int wa_staging_bytes(bool pair, bool fuse) { return wa_ewarps(fuse) * 16 * wa_stage_pitch(pair); }   // 16 pixel rows per warp
 
 // scale / shift per (image, channel) of a GroupNorm(8) over a virtual concat of up to two tensors:
 // coef[(n*C + c)*2] = rstd*gamma, coef[..+1] = beta - mean*rstd*gamma
@@ -157,7 +160,7 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, ui
 }
 
 template <bool PAIR, bool FUSE>
-__global__ void __launch_bounds__(FUSE ? WA_FUSE_THREADS : WA_THREADS, 1)
+__global__ void __launch_bounds__(wa_threads(FUSE), 1)
 conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA0b,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapW, const ConvParams p, const WaGeom g) {
@@ -170,7 +173,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int nblk_used = g.cch0 * g.slots0 + g.cch1a + g.cch1b + g.cchr;
     const int w_slots = g.resident ? nblk_used : g.w_stages;
     uint8_t* smem_o = smem_w + (size_t)w_slots * WA_BLK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + wa_staging_bytes(PAIR));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + wa_staging_bytes(PAIR, FUSE));
     uint64_t* xfull = bars;                       // TMA -> (transform | MMA)
     uint64_t* xready = xfull + g.a_stages;        // transform -> MMA (FUSE only)
     uint64_t* xempty = xready + g.a_stages;       // MMA -> TMA
@@ -186,7 +189,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < g.a_stages; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xready[s], WA_TWARPS); mbar_init(&xempty[s], 1); }
         for (int s = 0; s < g.w_stages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], WA_EWARPS); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], wa_ewarps(FUSE)); }
         mbar_fence_init();
     }
     // the row after each box must read as zero (tap (+1,+1) of the last position of the last box row lands there)
@@ -328,10 +331,10 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (++as == (uint32_t)g.tstages) { as = 0; aph ^= 1; }
             }
         }
-    } else if (FUSE && warp >= 4 + WA_EWARPS) {
+    } else if (FUSE && warp >= 4 + wa_ewarps(FUSE)) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===================== transform: GroupNorm(+SiLU) in place on every segment-0 box =====================
-        const int tt = threadIdx.x - (4 + WA_EWARPS) * 32;
+        const int tt = threadIdx.x - (4 + wa_ewarps(FUSE)) * 32;
         constexpr int PL = WA_TWARPS * 4;              // position lanes
         const int j = tt & 7, pl = tt >> 3;            // logical 16-byte vector (8 channels) / position lane
         const int npos = g.rows * g.pitch;
@@ -419,11 +422,26 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int t4 = lane & 3, t8 = lane >> 2;
         constexpr int SP = wa_stage_pitch(PAIR);
         constexpr int CV = PAIR ? 2 : 4;                     // channel sub-blocks of 8 per thread
-        constexpr int EQ = WA_EWARPS / 4;                    // warps per quarter
+        constexpr int EQ = wa_ewarps(FUSE) / 4;              // warps per quarter
         const uint32_t stage = smem_u32(smem_o + (warp - 4) * 16 * SP);
         const int nhu = g.N >> 4;
         const int HW = g.H * g.W;
         uint32_t as = 0, aph = 0;
+        // per-thread channels: cbase + 8*v + t8, v = 0..CV-1 (fragment rows t8 / t8+8 of the two 16-lane halves).  The per-channel
+        // addend (bias, or bias + time projection of the tile's image) of the NEXT tile is fetched while the current one is
+        // drained: loaded at the top of its own tile, the global-load latency sat on the epilogue's critical path (ncu: 7 % of
+        // the kernel's stall samples on that one line)
+        float addn[CV];
+        auto load_addend = [&](int tile_, float* dst) {
+            int mt_ = tile_, nt_ = 0;
+            if (g.n_tiles > 1) { mt_ = tile_ / g.n_tiles; nt_ = tile_ - mt_ * g.n_tiles; }
+            const int n_ = (int)__umulhi((uint32_t)mt_, g.inv_tpi);
+            const float* ab = p.temb ? p.temb + (size_t)n_ * p.temb_stride : p.bias;
+            const int cb_ = nt_ * g.ctile + q * (PAIR ? 16 : 32);
+#pragma unroll
+            for (int v = 0; v < CV; ++v) dst[v] = ab[cb_ + 8 * v + t8];
+        };
+        if ((int)blockIdx.x < total_tiles) load_addend(blockIdx.x, addn);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mt = tile, nt = 0;
             if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
@@ -431,13 +449,10 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int q0 = ti * g.adv;
             const int cbase = nt * g.ctile + q * (PAIR ? 16 : 32);   // first channel of this warp
             bf16* const obase = p.out + (size_t)n * HW * p.Cout + cbase;
-            // per-thread channels: cbase + 8*v + t8, v = 0..CV-1 (fragment rows t8 / t8+8 of the two 16-lane halves)
             float addv[CV], s1[CV], s2[CV];
-            {
-                const float* ab = p.temb ? p.temb + (size_t)n * p.temb_stride : p.bias;
 #pragma unroll
-                for (int v = 0; v < CV; ++v) { addv[v] = ab[cbase + 8 * v + t8]; s1[v] = 0.f; s2[v] = 0.f; }
-            }
+            for (int v = 0; v < CV; ++v) { addv[v] = addn[v]; s1[v] = 0.f; s2[v] = 0.f; }
+            if (tile + (int)gridDim.x < total_tiles) load_addend(tile + gridDim.x, addn);
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * g.tstride;

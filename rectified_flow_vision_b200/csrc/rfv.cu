@@ -408,7 +408,7 @@ struct rfv_engine {
     // Geometry and shared-memory plan of a weights-as-A conv (conv_wa.cuh).  Picks the tile width N (positions per tile) that
     // wastes the fewest MMA columns among those that keep the whole weight matrix resident; layers that have to stream their
     // weights take the widest tiles (weight blocks are re-fetched per tile).
-    int plan_wa(WaGeom* gp, size_t* smem, const ConvLayer* L, int W, int H, bool may_resid, int cch0a) {
+    int plan_wa(WaGeom* gp, size_t* smem, const ConvLayer* L, int W, int H, bool may_resid, int cch0a, bool fuse) {
         WaGeom& g = *gp;
         const bool pair = L->Cout % 128 != 0;
         g.W = W; g.H = H; g.pitch = W + 1;
@@ -420,7 +420,7 @@ struct rfv_engine {
         g.nblk = g.cch0 * g.slots0 + g.cch1a + g.cch1b + g.ctile / 64;
         g.inv_pitch = (uint32_t)((0x100000000ull + g.pitch - 1) / g.pitch);
         const int nblk_max = g.nblk - (may_resid ? 0 : g.ctile / 64);
-        const int avail = 227 * 1024 - 2048 - 512 - wa_staging_bytes(pair);
+        const int avail = 227 * 1024 - 2048 - 512 - wa_staging_bytes(pair, fuse);
         const int positions = H * g.pitch;
         double best = 1e30;
         int bestN = 0;
@@ -470,7 +470,7 @@ struct rfv_engine {
             g.a_stages = std::min(4, (avail - wregion) / g.stage_bytes);
         }
         if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: weights-as-A tile does not fit shared memory", L->name.c_str());
-        *smem = 2048 + (size_t)g.a_stages * g.stage_bytes + wregion + wa_staging_bytes(pair) + 512;
+        *smem = 2048 + (size_t)g.a_stages * g.stage_bytes + wregion + wa_staging_bytes(pair, fuse) + 512;
         return 0;
     }
     // allocate the block-layout weight copy of a layer and chain its refresh behind the repack of the parameters it derives from
@@ -526,7 +526,7 @@ struct rfv_engine {
             WaGeom& g = bd->g;
             bd->pair = L->Cout % 128 != 0;
             bd->fuse = fr != nullptr;
-            RFV_TRY(plan_wa(&g, &bd->smem, L, out->W, out->H, resid != nullptr || acc_of != nullptr, in0->C / 64));
+            RFV_TRY(plan_wa(&g, &bd->smem, L, out->W, out->H, resid != nullptr || acc_of != nullptr, in0->C / 64, fr != nullptr));
             RFV_TRY(ensure_wa(L, g));
             auto amap = [&](CUtensorMap* m, const ActP& t) {
                 return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rs, 1);
@@ -552,11 +552,11 @@ struct rfv_engine {
                 g.m_tiles = rc.B * g.tiles_per_img;
                 const int grid = std::min(g.m_tiles * g.n_tiles, sms);
                 if (bd->fuse) {
-                    if (bd->pair) conv_wa_kernel<true, true><<<grid, WA_FUSE_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                    else conv_wa_kernel<false, true><<<grid, WA_FUSE_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    if (bd->pair) conv_wa_kernel<true, true><<<grid, wa_threads(true), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    else conv_wa_kernel<false, true><<<grid, wa_threads(true), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
                 } else {
-                    if (bd->pair) conv_wa_kernel<true, false><<<grid, WA_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                    else conv_wa_kernel<false, false><<<grid, WA_THREADS, bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    if (bd->pair) conv_wa_kernel<true, false><<<grid, wa_threads(false), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
+                    else conv_wa_kernel<false, false><<<grid, wa_threads(false), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
                 }
                 return cudaGetLastError();
             });

