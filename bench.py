@@ -379,7 +379,7 @@ def run_ours(args):
     e2e_gather = None
     if world > 1:
         from rectified_flow_vision_b200 import dist as rdist
-        job_noise = rdist.seeded_noise(world * P, CH, IMAGE, IMAGE, seed=4242).pin_memory()   # identical on every rank
+        job_noise = rdist.seeded_noise(world * P, CH, IMAGE, seed=4242).pin_memory()   # identical on every rank
         rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True)   # warm (NCCL channels)
         barrier()
         t0 = time.perf_counter()
