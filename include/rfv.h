@@ -85,6 +85,8 @@ typedef struct {
 #define RFV_FLAG_NO_WA     1048576 /* 3x3 stride-1 convs at the 32/64/128-pixel levels: do not use the weights-as-A kernel (conv_wa.cuh:
                                     * A = 128-row weight block, B = up to 256 pixels), fall back to the per-tap implicit-GEMM kernel
                                     * (conv_umma.cuh) that serves every other conv shape (A/B) */
+#define RFV_FLAG_NO_GRAPH  4194304 /* Euler loops: enqueue every kernel of every step directly instead of replaying the captured
+                                    * CUDA graph of the whole N-step loop of a micro-batch (A/B; profiling mode does so too) */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

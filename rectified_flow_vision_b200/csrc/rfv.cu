@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <vector>
@@ -214,6 +215,11 @@ struct rfv_engine {
     // kernels (GroupNorm apply, thin convs) run under the other chain's tensor-bound convolutions.  Created on first use.
     rfv_engine* lane = nullptr;
     bool use_lanes = true;     // RFV_FLAG_ONE_LANE clears it
+    // Whole-loop executor: the N-step Euler loop of one micro-batch (time-table fill + N x ~69 launches on fixed engine-owned
+    // buffers) is captured once per (rows, steps, state buffer) and replayed as ONE graph launch.
+    struct LoopGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    std::map<std::tuple<int, int, int>, LoopGraph> loop_graphs;
+    bool use_graphs = true;    // RFV_FLAG_NO_GRAPH clears it
     cudaEvent_t ev_fork = nullptr, ev_join[2]{};
     RunCtx fwd_rc;             // rfv_train_forward's context, replayed by rfv_train_backward
     bool have_fwd = false;
@@ -233,6 +239,7 @@ struct rfv_engine {
 
     ~rfv_engine() {
         delete lane;
+        for (auto& kv : loop_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& e : ev_join) if (e) cudaEventDestroy(e);
         for (void* p : allocs) cudaFree(p);
@@ -1743,6 +1750,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->keep_acts = (cfg->flags & RFV_FLAG_KEEP_ACTS) != 0;
     e->use_wa = !(cfg->flags & RFV_FLAG_NO_WA);
     e->use_lanes = !(cfg->flags & RFV_FLAG_ONE_LANE) && !(cfg->flags & RFV_FLAG_TRAIN);
+    e->use_graphs = !(cfg->flags & RFV_FLAG_NO_GRAPH);
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
     e->fuse_mode = (cfg->flags & RFV_FLAG_FUSE_GN) ? 2 : ((cfg->flags & RFV_FLAG_NO_FUSE_GN) ? 0 : 1);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;
@@ -1931,6 +1939,36 @@ static int euler_chunk(rfv_handle h, float* x, int B, int num_steps, float* traj
     return 0;
 }
 
+// The Euler loop of the micro-batch held in e->xbuf[buf] as one CUDA-graph launch on `s` (a non-default stream).  *done = false:
+// the loop is not graph-able here (disabled, profiling, too many nodes, capture failed) and the caller enqueues it step by step.
+static int euler_chunk_graph(rfv_engine* e, cudaStream_t s, int buf, int B, int num_steps, bool* done) {
+    *done = false;
+    if (!e->use_graphs || e->profiling || (size_t)num_steps * e->ops.size() > 16384) return 0;
+    const auto key = std::make_tuple(B, num_steps, buf);
+    auto it = e->loop_graphs.find(key);
+    if (it == e->loop_graphs.end()) {
+        if (e->loop_graphs.size() >= 32) return 0;
+        rfv_engine::LoopGraph lg;
+        const int64_t before = e->launches;
+        cudaGraph_t gr = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+        const int rc = euler_chunk(e, e->xbuf[buf], B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &gr);
+        lg.launches = e->launches - before;
+        e->launches = before;
+        if (rc == 0 && ce == cudaSuccess && gr && cudaGraphInstantiate(&lg.exec, gr, 0) != cudaSuccess) lg.exec = nullptr;
+        if (gr) cudaGraphDestroy(gr);
+        cudaGetLastError();
+        if (rc != 0 || ce != cudaSuccess) lg.exec = nullptr;   // remembered: this shape is enqueued directly from now on
+        it = e->loop_graphs.emplace(key, lg).first;
+    }
+    if (!it->second.exec) return 0;
+    CU_CHECK(cudaGraphLaunch(it->second.exec, s));
+    e->launches += it->second.launches;
+    *done = true;
+    return 0;
+}
+
 // the twin engine of the second lane: same configuration, weights copied device-to-device from this engine's fp32 masters
 static int ensure_lane(rfv_handle h, cudaStream_t s) {
     if (h->lane) return 0;
@@ -1968,6 +2006,14 @@ static int run_two_lanes(rfv_handle h, int64_t n, int num_steps, cudaStream_t s0
                 const int B = (int)std::min<int64_t>(h->cap, n - b0);
                 float* x = nullptr;
                 RFV_TRY(begin((int)(&l - ln), l.e, l.k, b0, B, &x));
+                // state in one of the engine's own buffers: the whole loop is one graph launch
+                bool whole = false;
+                if (x == l.e->xbuf[0] || x == l.e->xbuf[1]) RFV_TRY(euler_chunk_graph(l.e, l.s, x == l.e->xbuf[1] ? 1 : 0, B, num_steps, &whole));
+                if (whole) {
+                    RFV_TRY(end((int)(&l - ln), l.e, l.k, b0, B));
+                    ++l.c; ++l.k;
+                    continue;
+                }
                 l.run = EulerRun{};
                 l.run.e = l.e; l.run.s = l.s; l.run.x = x; l.run.B = B; l.run.num_steps = num_steps;
                 RFV_TRY(euler_begin(l.run));
@@ -1997,14 +2043,43 @@ RFV_EXPORT int rfv_euler_sample(rfv_handle h, float* x, int64_t batch, int num_s
         CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_fork, 0));
         CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->ev_fork, 0));
         CU_CHECK(cudaStreamWaitEvent(h->lane->s_cmp, h->lane->ev_weights, 0));
+        // with the loop executor the chunk is staged through the engine's own state buffer (two device-to-device copies of
+        // the chunk against hundreds of launches): captured graphs need fixed addresses
+        const bool staged = h->use_graphs;
         RFV_TRY(run_two_lanes(h, batch, num_steps, h->s_cmp, h->lane->s_cmp,
-            [&](int, rfv_engine*, int64_t, int64_t b0, int, float** xo) { *xo = x + b0 * ie; return 0; },
-            [&](int, rfv_engine*, int64_t, int64_t, int) { return 0; }));
+            [&](int, rfv_engine* e, int64_t, int64_t b0, int B, float** xo) {
+                if (!staged) { *xo = x + b0 * ie; return 0; }
+                CU_CHECK(cudaMemcpyAsync(e->xbuf[0], x + b0 * ie, (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToDevice, e->s_cmp));
+                *xo = e->xbuf[0];
+                return 0;
+            },
+            [&](int, rfv_engine* e, int64_t, int64_t b0, int B) {
+                if (staged) CU_CHECK(cudaMemcpyAsync(x + b0 * ie, e->xbuf[0], (size_t)B * ie * sizeof(float), cudaMemcpyDeviceToDevice, e->s_cmp));
+                return 0;
+            }));
         // ... join: the caller's stream continues when both chains are done
         CU_CHECK(cudaEventRecord(h->ev_join[0], h->s_cmp));
         CU_CHECK(cudaEventRecord(h->ev_join[1], h->lane->s_cmp));
         CU_CHECK(cudaStreamWaitEvent(s, h->ev_join[0], 0));
         CU_CHECK(cudaStreamWaitEvent(s, h->ev_join[1], 0));
+        return h->leave(s);
+    }
+    if (!traj && h->use_graphs && !h->profiling) {
+        // one chain on the engine's compute stream (a captured graph cannot be recorded on the legacy default stream a caller
+        // may hand in): fork, stage each chunk through xbuf[0], replay the loop graph, join
+        CU_CHECK(cudaEventRecord(h->ev_fork, s));
+        CU_CHECK(cudaStreamWaitEvent(h->s_cmp, h->ev_fork, 0));
+        for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
+            const int B = (int)std::min<int64_t>(h->cap, batch - b0);
+            const size_t bytes = (size_t)B * ie * sizeof(float);
+            CU_CHECK(cudaMemcpyAsync(h->xbuf[0], x + b0 * ie, bytes, cudaMemcpyDeviceToDevice, h->s_cmp));
+            bool whole = false;
+            RFV_TRY(euler_chunk_graph(h, h->s_cmp, 0, B, num_steps, &whole));
+            if (!whole) RFV_TRY(euler_chunk(h, h->xbuf[0], B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
+            CU_CHECK(cudaMemcpyAsync(x + b0 * ie, h->xbuf[0], bytes, cudaMemcpyDeviceToDevice, h->s_cmp));
+        }
+        CU_CHECK(cudaEventRecord(h->ev_join[0], h->s_cmp));
+        CU_CHECK(cudaStreamWaitEvent(s, h->ev_join[0], 0));
         return h->leave(s);
     }
     for (int64_t b0 = 0; b0 < batch; b0 += h->cap) {
@@ -2054,7 +2129,9 @@ RFV_EXPORT int rfv_euler_sample_host(rfv_handle h, const float* noise_host, floa
             const int B = (int)std::min<int64_t>(h->cap, n - b0);
             float* xd = nullptr;
             RFV_TRY(begin(0, h, k, b0, B, &xd));
-            RFV_TRY(euler_chunk(h, xd, B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
+            bool whole = false;
+            RFV_TRY(euler_chunk_graph(h, h->s_cmp, (int)(k & 1), B, num_steps, &whole));
+            if (!whole) RFV_TRY(euler_chunk(h, xd, B, num_steps, nullptr, 0, 0, nullptr, nullptr, nullptr, h->s_cmp));
             RFV_TRY(end(0, h, k, b0, B));
         }
     }

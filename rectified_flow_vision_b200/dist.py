@@ -43,8 +43,9 @@ def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, 
     width = -(-n // world)  # equal-sized slots for the collective; short shards are padded
     shape = tuple(local.shape[1:])
     if backend == "nccl":
-        # device all-gather over NVLink, then ONE device->host copy into a pinned buffer (a pageable .cpu() of the gathered
-        # tensor runs at a few GB/s and would cost more than the collective)
+        # device all-gather over NVLink, then ONE device->host copy.  Small results land in a pinned buffer; beyond 256 MB the
+        # page-locking of a fresh buffer (every rank of the box doing it at once) costs more than the driver's staged copy
+        # into pageable memory
         dev = torch.device("cuda", torch.cuda.current_device())
         gathered_dev = torch.empty((world * width,) + shape, dtype=local.dtype, device=dev)
         slot = gathered_dev[rank * width:(rank + 1) * width]      # gather in place: this rank's slot is its own input
@@ -52,7 +53,8 @@ def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, 
         if hi - lo < width:
             slot[hi - lo:].zero_()
         dist.all_gather_into_tensor(gathered_dev, slot, group=group)
-        gathered = torch.empty(gathered_dev.shape, dtype=local.dtype, pin_memory=True)
+        nbytes = gathered_dev.numel() * gathered_dev.element_size()
+        gathered = torch.empty(gathered_dev.shape, dtype=local.dtype, pin_memory=nbytes <= (256 << 20))
         gathered.copy_(gathered_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         del gathered_dev

@@ -18,6 +18,7 @@ from . import _build
 RFV_MAX_LEVELS = 8
 FLAG_NO_UMMA = 1
 FLAG_ONE_LANE = 2
+FLAG_NO_GRAPH = 4194304
 FLAG_KEEP_ACTS = 4
 FLAG_TRAIN = 32
 
