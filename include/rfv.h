@@ -171,9 +171,16 @@ int rfv_train_backward(rfv_handle h, const float* dv, int64_t batch, void* strea
 /* Zero the AdamW moments (a fresh torch.optim.AdamW, as every train_* call of the reference builds:
  * models/rectified_flow.py:208, models/base_flow.py:255).  The step counter lives with the caller (rfv_adamw.step). */
 int rfv_reset_optimizer(rfv_handle h, void* stream);
-/* The flat fp32 gradient buffer (device memory owned by the engine; one slot per parameter tensor in
- * rfv_tensor_info order; conv-weight slots are laid out [O][kh*kw][I]). */
+/* The flat fp32 gradient buffer (device memory owned by the engine; one slot per parameter tensor, laid out in the order the
+ * gradients become final during the backward pass; conv-weight slots are [O][kh*kw][I]; rfv_get_grad reads one tensor). */
 int rfv_grad_buffer(rfv_handle h, float** dev_ptr, int64_t* numel);
+/* Data-parallel overlap: the buffer is cut into rfv_grad_bucket_count contiguous ranges in completion order.
+ * rfv_grad_bucket_wait makes `stream` wait until range `index` of the LAST rfv_train_accumulate call is final, so a caller
+ * can enqueue the all-reduce of a finished range on a side stream while the rest of the backward pass still runs
+ * (models have no collective in the reference; this is the hook for "bucketed, overlapped" gradient all-reduce). */
+int rfv_grad_bucket_count(rfv_handle h);
+int rfv_grad_bucket_info(rfv_handle h, int index, int64_t* offset, int64_t* numel);
+int rfv_grad_bucket_wait(rfv_handle h, int index, void* stream);
 /* One parameter's gradient, scaled, in reference layout (tests / debugging). */
 int rfv_get_grad(rfv_handle h, const char* name, float* dev_ptr, int64_t numel, float scale, void* stream);
 /* Make the optimizer also write updated values into caller-owned fp32 storage (the torch Parameter). */

@@ -84,6 +84,7 @@ struct Param {  // one reference state_dict tensor
     std::function<int(cudaStream_t)> repack;  // refresh derived buffers after upload
     std::function<int(float*, cudaStream_t)> readback;  // optional: reconstruct fp32 from the packed form
     int64_t goff = 0;        // training: offset of this tensor's slot in the flat gradient / Adam-moment buffers
+    int final_block = 1 << 30;   // training: backward block after which this tensor's gradient is final (blocks run back to front)
     int O = 0, I = 0, KK = 0;  // conv weights (KK > 1): the slot is laid out [O][KK][I] (what the wgrad kernel writes)
     float* bound = nullptr;  // caller-owned fp32 storage (torch Parameter) the optimizer also writes
 };
@@ -221,6 +222,14 @@ struct rfv_engine {
     std::map<std::tuple<int, int, int>, LoopGraph> loop_graphs;
     bool use_graphs = true;    // RFV_FLAG_NO_GRAPH clears it
     cudaEvent_t ev_fork = nullptr, ev_join[2]{};
+    // Gradient buckets for a data-parallel caller: slots are laid out in the order their gradients become final during the
+    // backward pass, and cut into a few contiguous ranges; run_backward records, per bucket, an event on each backward stream
+    // once the last block that writes into the range has been enqueued, so the caller can all-reduce a finished range while
+    // the rest of the backward pass still runs.
+    struct GradBucket { int64_t off = 0, numel = 0; int ready_block = 0; cudaEvent_t ev[2] = {nullptr, nullptr}; };
+    std::vector<GradBucket> buckets;
+    int temb_block = 0;
+    bool buckets_valid = false;   // the events belong to the last backward pass of the last rfv_train_accumulate
     RunCtx fwd_rc;             // rfv_train_forward's context, replayed by rfv_train_backward
     bool have_fwd = false;
     bool two_streams = true;   // RFV_FLAG_ONE_STREAM: run the whole backward pass on one stream (A/B testing)
@@ -239,6 +248,7 @@ struct rfv_engine {
 
     ~rfv_engine() {
         delete lane;
+        for (auto& b : buckets) for (auto& e : b.ev) if (e) cudaEventDestroy(e);
         for (auto& kv : loop_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& e : ev_join) if (e) cudaEventDestroy(e);
@@ -866,6 +876,11 @@ struct rfv_engine {
     void on_side(bool wait_main) { cur_lane = 1; if (wait_main) pending_side_sync = true; }
     void on_main() { cur_lane = 0; }
     float* gslot(int pi) { return gflat + params[pi].goff; }  // run time only (the flat buffer is allocated after the plan)
+    // record time: the op being recorded writes parameter pi's gradient; the LAST block to do so (lowest index: blocks run back
+    // to front) decides when the slot is final -- the order the slots are laid out in and the gradient buckets are cut by
+    void mark_grad(int pi) {
+        if (pi >= 0 && !bwd_blocks.empty()) params[pi].final_block = std::min(params[pi].final_block, (int)bwd_blocks.size() - 1);
+    }
 
     int ensure_grad(const ActP& a) {
         if (a->grad) return 0;
@@ -951,6 +966,7 @@ struct rfv_engine {
         const int taps = kind == 1 ? 1 : 9;
         const double fl = 2.0 * taps * a->C * Cout * Ho * Wo * (kind == 3 ? 4 : 1);  // algorithmic (kind 3: at the high resolution)
         const int sms = num_sms;
+        if (!dst_override) mark_grad(pi);
         push("wgrad_umma", "bwd:wgrad:" + label, fl, [this, bd, pi, sms, dst_override](const RunCtx& rc, cudaStream_t s) {
             WgradGeom g = bd->g;
             g.num_tiles = rc.B * g.tiles_per_img;
@@ -969,6 +985,8 @@ struct rfv_engine {
         const int vpp = C / 8;
         const int threads = (256 / vpp) * vpp;
         const int ppb = std::min(HW, std::max(1, 32768 / C));
+        mark_grad(pi1);
+        mark_grad(pi2);
         push("colsum", "bwd:colsum:" + label, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
             dim3 grid((HW + ppb - 1) / ppb, rc.B);
             colsum_kernel<<<grid, threads, C * sizeof(float), s>>>(dy, out_nc, ld_nc, pi1 >= 0 ? gslot(pi1) : nullptr,
@@ -1001,6 +1019,8 @@ struct rfv_engine {
         a.pix_per_block = std::min(st.HW, std::max(1, 65536 / C));
         const bool drop = st.drop;
         const int id = st.id, ig = st.ig, ib = st.ib;
+        mark_grad(ig);
+        mark_grad(ib);
         ActP sa = st.srcs[0], sb = st.srcs.size() > 1 ? st.srcs[1] : nullptr;
         const bool over = out_override != nullptr;
         auto fill = [=](GnBwdArgs& q, const RunCtx& rc) {
@@ -1058,7 +1078,7 @@ struct rfv_engine {
 
     int build();
     int finish_training_setup();
-    int run_backward(const RunCtx& rc, cudaStream_t s);
+    int run_backward(const RunCtx& rc, cudaStream_t s, bool record_buckets = false);
     int run_forward(const RunCtx& rc, cudaStream_t s);
 };
 
@@ -1157,6 +1177,9 @@ int rfv_engine::build() {
             // backward of the time MLP: runs last (first block recorded), after every ResidualBlock has added its
             // d(time projection) rows into d_tproj.  Needs per-row t (training always passes a t vector).
             begin_bwd();
+            // (the per-block projections are registered later: finish_training_setup marks them as final in this block)
+            mark_grad(tw1); mark_grad(tb1); mark_grad(tw2); mark_grad(tb2);
+            temb_block = (int)bwd_blocks.size() - 1;
             push("temb_bwd", "bwd:temb", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
                 const int B = rc.B;
                 // dW_block = d_tproj[:, off:off+C]^T . temb_act ; biases (+ conv1.bias) = column sums: all blocks in one launch
@@ -1257,6 +1280,7 @@ int rfv_engine::build() {
             }
             on_side(true);
             RFV_TRY(bwd_wgrad("input_conv", 0, xpad, dh, mc, S, S, iw, 9 * 64, 0, wscr));
+            mark_grad(iw);
             push("elementwise_bwd", "bwd:extract:input_conv", 0.0, [=](const RunCtx&, cudaStream_t s) {
                 extract_wgrad_kernel<<<(mc * Cin * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), mc, Cin, 64);
                 return cudaGetLastError();
@@ -1523,6 +1547,7 @@ int rfv_engine::build() {
             RFV_TRY(scratch_act(&dvpad, 1, 64, S, S));
             {
                 bf16* dp = dvpad->p;
+                mark_grad(ib);
                 push("elementwise_bwd", "bwd:pad:output_conv.2", 0.0, [=](const RunCtx& rc, cudaStream_t s) {
                     cudaError_t e = cudaMemsetAsync(wscr, 0, (size_t)64 * 9 * C * sizeof(float), s);
                     if (e != cudaSuccess) return e;
@@ -1533,6 +1558,7 @@ int rfv_engine::build() {
             }
             on_side(true);
             RFV_TRY(bwd_wgrad("output_conv.2", 0, a, dvpad->p, 64, S, S, iw, 9 * C, 0, wscr));
+            mark_grad(iw);
             push("elementwise_bwd", "bwd:extract:output_conv.2", 0.0, [=](const RunCtx&, cudaStream_t s) {
                 extract_wgrad_kernel<<<(Co * C * 9 + 255) / 256, 256, 0, s>>>(wscr, gslot(iw), Co, C, C);
                 return cudaGetLastError();
@@ -1635,6 +1661,34 @@ int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
 // training: flat buffers, backward driver
 // ---------------------------------------------------------------------------------------------------------
 int rfv_engine::finish_training_setup() {
+    // the time-MLP backward (recorded first, run last) also writes every block's projection weights / biases and conv1 biases
+    for (auto& tp : time_projs)
+        for (int pi : {tp.iw, tp.ib, tp.icb}) params[pi].final_block = std::min(params[pi].final_block, temb_block);
+    for (auto& pr : params)
+        if (pr.final_block == (1 << 30)) return fail(RFV_ERR_STATE, "internal: no backward op writes the gradient of %s", pr.name.c_str());
+    {   // slots in completion order (stable within a block), then ~4 buckets of similar size cut at block boundaries
+        std::vector<int> order(params.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return params[a].final_block > params[b].final_block; });
+        int64_t off = 0;
+        const int64_t target = gtotal / 4;
+        GradBucket cur;
+        for (size_t k = 0; k < order.size(); ++k) {
+            Param& pr = params[order[k]];
+            pr.goff = off;
+            off += pr.numel;
+            cur.numel += pr.numel;
+            cur.ready_block = std::min<int>(pr.final_block, (int)bwd_blocks.size() - 1);
+            const bool last = k + 1 == order.size();
+            if (last || (cur.numel >= target && params[order[k + 1]].final_block != pr.final_block)) {
+                buckets.push_back(cur);
+                cur = GradBucket{};
+                cur.off = off;
+            }
+        }
+        for (auto& b : buckets)
+            for (auto& e : b.ev) CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     RFV_TRY(dalloc(&gflat, (size_t)gtotal));
     RFV_TRY(dalloc(&mflat, (size_t)gtotal));
     RFV_TRY(dalloc(&vflat, (size_t)gtotal));
@@ -1667,7 +1721,7 @@ static AdamSeg make_seg(const Param& p) {
     return s;
 }
 
-int rfv_engine::run_backward(const RunCtx& rc, cudaStream_t s) {
+int rfv_engine::run_backward(const RunCtx& rc, cudaStream_t s, bool record_buckets) {
     // hand over from the caller's stream to the engine's two backward streams (main: high priority, side: low)
     CU_CHECK(cudaEventRecord(ev_bwd[0], s));
     CU_CHECK(cudaStreamWaitEvent(s_bwd, ev_bwd[0], 0));
@@ -1699,7 +1753,14 @@ int rfv_engine::run_backward(const RunCtx& rc, cudaStream_t s) {
                 bwd_prof.push_back({&op, e0, e1});
             }
         }
+        if (record_buckets)
+            for (auto& b : buckets)
+                if (b.ready_block == (int)bi) {   // everything that writes into this range is enqueued: one event per stream
+                    CU_CHECK(cudaEventRecord(b.ev[0], s_bwd));
+                    CU_CHECK(cudaEventRecord(b.ev[1], two_streams ? s_side : s_bwd));
+                }
     }
+    buckets_valid = record_buckets;
     CU_CHECK(cudaEventRecord(ev_bwd[2], s_side));
     CU_CHECK(cudaStreamWaitEvent(s_bwd, ev_bwd[2], 0));
     CU_CHECK(cudaEventRecord(ev_bwd[3], s_bwd));
@@ -2204,7 +2265,7 @@ RFV_EXPORT int rfv_train_accumulate(rfv_handle h, const float* x0, const float* 
         rc.drop_scale = rc.drop_thresh ? (float)(1.0 / (1.0 - (double)rc.drop_thresh / 65536.0)) : 1.f;
         rc.seed = mix_seed(seed, (uint32_t)idx);
         RFV_TRY(h->run_forward(rc, s));
-        RFV_TRY(h->run_backward(rc, s));
+        RFV_TRY(h->run_backward(rc, s, b0 + h->cap >= batch));   // the last chunk completes the gradients: bucket events
     }
     h->have_fwd = false;   // the kept activations no longer belong to an rfv_train_forward call
     scale_kernel<<<1, 32, 0, s>>>(loss_out, 1, 1.0f / (float)((double)batch * ie));
@@ -2262,6 +2323,22 @@ RFV_EXPORT int rfv_grad_buffer(rfv_handle h, float** dev_ptr, int64_t* numel) {
     if (!h->train) return fail(RFV_ERR_STATE, "engine was not created with RFV_FLAG_TRAIN");
     *dev_ptr = h->gflat;
     *numel = h->gtotal;
+    return 0;
+}
+
+RFV_EXPORT int rfv_grad_bucket_count(rfv_handle h) { return (h && h->train) ? (int)h->buckets.size() : 0; }
+
+RFV_EXPORT int rfv_grad_bucket_info(rfv_handle h, int index, int64_t* offset, int64_t* numel) {
+    if (!h || !h->train || index < 0 || index >= (int)h->buckets.size()) return fail(RFV_ERR_INVALID, "gradient bucket index out of range");
+    if (offset) *offset = h->buckets[index].off;
+    if (numel) *numel = h->buckets[index].numel;
+    return 0;
+}
+
+RFV_EXPORT int rfv_grad_bucket_wait(rfv_handle h, int index, void* stream) {
+    if (!h || !h->train || index < 0 || index >= (int)h->buckets.size()) return fail(RFV_ERR_INVALID, "gradient bucket index out of range");
+    if (!h->buckets_valid) return fail(RFV_ERR_STATE, "no rfv_train_accumulate has recorded bucket events yet");
+    for (auto& e : h->buckets[index].ev) CU_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, e, 0));
     return 0;
 }
 

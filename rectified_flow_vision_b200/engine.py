@@ -68,6 +68,9 @@ SYMBOLS = {
     "rfv_train_backward": (C.c_int, [_VP, _FP, _I64, _VP]),
     "rfv_reset_optimizer": (C.c_int, [_VP, _VP]),
     "rfv_grad_buffer": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_I64)]),
+    "rfv_grad_bucket_count": (C.c_int, [_VP]),
+    "rfv_grad_bucket_info": (C.c_int, [_VP, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
+    "rfv_grad_bucket_wait": (C.c_int, [_VP, C.c_int, _VP]),
     "rfv_get_grad": (C.c_int, [_VP, C.c_char_p, _FP, _I64, C.c_float, _VP]),
     "rfv_bind_param": (C.c_int, [_VP, C.c_char_p, _FP]),
     "rfv_optimizer_step": (C.c_int, [_VP, C.POINTER(RfvAdamW), _FP, _VP]),
@@ -352,6 +355,19 @@ class Engine:
         ptr, n = _VP(), _I64()
         _check(self.lib.rfv_grad_buffer(self.h, C.byref(ptr), C.byref(n)))
         return torch.as_tensor(_DeviceArray(ptr.value, n.value), device=self.device)
+
+    def grad_buckets(self):
+        """[(offset, numel)] of the contiguous ranges of the flat gradient buffer, in the order they become final."""
+        out = []
+        off, n = _I64(), _I64()
+        for k in range(int(self.lib.rfv_grad_bucket_count(self.h))):
+            _check(self.lib.rfv_grad_bucket_info(self.h, k, C.byref(off), C.byref(n)))
+            out.append((off.value, n.value))
+        return out
+
+    def grad_bucket_wait(self, index: int, stream: "torch.cuda.Stream") -> None:
+        """`stream` waits until bucket `index` of the last ``train_accumulate`` is final."""
+        _check(self.lib.rfv_grad_bucket_wait(self.h, int(index), C.c_void_p(stream.cuda_stream)))
 
     def get_grad(self, name: str, numel: int, scale: float = 1.0) -> torch.Tensor:
         out = torch.empty(numel, dtype=torch.float32, device=self.device)

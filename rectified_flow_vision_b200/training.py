@@ -37,6 +37,7 @@ class NativeTrainer:
         self.process_group = process_group
         self._micro_batch = micro_batch
         self.last_grad_norm = None
+        self._comm_stream = None
 
     def _engine(self, size: int):
         return self.model.velocity_net.train_engine(size, torch.device(self.model.device), self._micro_batch)
@@ -52,6 +53,29 @@ class NativeTrainer:
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self.process_group)
         return 1
+
+    def _all_reduce_gradients(self, eng) -> None:
+        """SUM over the ranks of the flat gradient buffer.  On NCCL the buffer is reduced bucket by bucket on a side stream: the
+        engine lays the slots out in the order they become final and exposes one event pair per bucket, so the collective of
+        a finished range runs under the rest of the backward pass (everything is enqueued asynchronously: the backward pass
+        is already in the stream queues when the first wait is placed).  RFV_BUCKETS=0 or a non-NCCL group: one call."""
+        import os
+        import torch.distributed as dist
+        buf = eng.grad_buffer()
+        buckets = eng.grad_buckets() if hasattr(eng, "grad_buckets") else []
+        overlap = (len(buckets) > 1 and buf.is_cuda and dist.get_backend(self.process_group) == "nccl"
+                   and os.environ.get("RFV_BUCKETS", "1") != "0")
+        if not overlap:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.process_group)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(buf.device)
+        cur = torch.cuda.current_stream(buf.device)
+        for k, (off, n) in enumerate(buckets):
+            eng.grad_bucket_wait(k, self._comm_stream)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(buf[off:off + n], op=dist.ReduceOp.SUM, group=self.process_group)
+        cur.wait_stream(self._comm_stream)
 
     def step(self, x0: torch.Tensor, x1: torch.Tensor, t: torch.Tensor, lr: Optional[float] = None,
              dropout: Optional[float] = None, seed: Optional[int] = None) -> torch.Tensor:
@@ -72,8 +96,7 @@ class NativeTrainer:
         eng.zero_grad()
         loss = eng.train_accumulate(x0, x1, t, dropout_p=p, seed=seed)
         if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(eng.grad_buffer(), op=dist.ReduceOp.SUM, group=self.process_group)
+            self._all_reduce_gradients(eng)
         self.last_grad_norm = eng.optimizer_step(self.lr if lr is None else lr, self.step_count, self.betas[0],
                                                  self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
                                                  grad_scale=1.0 / world)

@@ -295,3 +295,38 @@ def test_training_curve_tracks_pytorch_autograd():
     num = sum(float(((sd[k].detach() - P[k].detach()) ** 2).sum()) for k in P)
     den = sum(float(((P[k].detach() - p0[k]) ** 2).sum()) for k in P)
     assert (num / den) ** 0.5 <= 0.15, (num / den) ** 0.5
+
+
+def test_gradient_buckets_cover_the_buffer_and_signal_completion():
+    """Data-parallel overlap hook (include/rfv.h rfv_grad_bucket_*): the buckets tile the flat gradient buffer exactly, in the
+    order the gradients become final; a side stream that waits on every bucket of the last train_accumulate sees the same
+    gradients as the caller's stream does after the call."""
+    m, x0, x1, t, tg = _setup("small32")
+    eng = m.velocity_net.train_engine(32, "cuda:0", micro_batch=4)
+    buckets = eng.grad_buckets()
+    buf = eng.grad_buffer()
+    assert 2 <= len(buckets) <= 8
+    pos = 0
+    for off, n in buckets:
+        assert off == pos and n > 0
+        pos += n
+    assert pos == buf.numel() == sum(p.numel() for p in m.parameters())
+    side = torch.cuda.Stream("cuda:0")
+    eng.zero_grad()
+    eng.train_accumulate(x0, x1, t, dropout_p=0.0, seed=1)
+    snap = []
+    for k, (off, n) in enumerate(buckets):       # enqueued while the backward pass may still be running
+        eng.grad_bucket_wait(k, side)
+        with torch.cuda.stream(side):
+            snap.append(buf[off:off + n].clone())
+    side.synchronize()
+    torch.cuda.synchronize()
+    final = buf.clone()
+    for (off, n), sn in zip(buckets, snap):
+        assert torch.equal(sn, final[off:off + n]), "a bucket was read before its gradients were final"
+    keys = [f[len("grad_full/"):] for f in tg.files if f.startswith("grad_full/")]
+    assert keys
+    sd = dict(m.named_parameters())
+    for key in keys:                                  # the re-ordered slots still map to the right tensors
+        g = eng.get_grad(key, sd[key].numel()).cpu().numpy()
+        assert util.rel_l2(g.reshape(-1), tg["grad_full/" + key].reshape(-1)) <= TOL_GRAD_L2, key
