@@ -98,8 +98,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
+// Optional suspend-time hint of a try_wait (ns): the waiting thread sleeps in hardware until the phase completes or the hint
+// expires.  Without a hint every waiting warp re-polls about every 150 cycles -- ncu on a 64->64 conv_wa layer: 21 % of all
+// executed warp instructions are these polls.  Measured same-box A/B (tools/ab_lib.sh, -DRFV_MBAR_HINT_NS=20000 against 0):
+// no difference in any kernel class (forward 8.22 vs 8.21 ms), so the polls cost nothing that matters; default off.
+#ifndef RFV_MBAR_HINT_NS
+#define RFV_MBAR_HINT_NS 0
+#endif
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = RFV_MBAR_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if RFV_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -107,6 +124,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

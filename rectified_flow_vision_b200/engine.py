@@ -85,7 +85,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return str(_build.LIB)
+    # RFV_LIB: an alternative build of the same sources (A/B measurements of compile-time switches on one GPU box)
+    return os.environ.get("RFV_LIB") or str(_build.LIB)
 
 
 def load_library():
