@@ -1356,15 +1356,22 @@ int rfv_engine::build() {
             const float sl2 = (1.0f / std::sqrt((float)d)) * 1.4426950408889634f;
             // tcgen05 kernel for the default shape (256 tokens, head dim 64); the mma.sync kernel covers the rest
             const bool au = use_umma && d == 64 && N == 256 && !(cfg.flags & RFV_FLAG_NO_ATTN_UMMA);
+            // longer sequences (1024 tokens at 128x128): the same core looped over 256-key blocks with the online softmax
+            const bool ak = use_umma && d == 64 && N > 256 && N % 256 == 0 && !(cfg.flags & RFV_FLAG_NO_ATTN_UMMA);
             auto amap = std::make_shared<CUtensorMap>();
-            if (au) {
+            if (au || ak) {
                 RFV_TRY(make_map2(amap.get(), qkv->p, 3 * C, cap * N, 128));
                 CU_CHECK(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AU_SMEM));
+                CU_CHECK(cudaFuncSetAttribute(attn_umma_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AK_SMEM));
             }
             push("attention", "attn:mid_attn", 4.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
                 float* l = rc.train ? lse : nullptr;
                 if (au) {
                     attn_umma_kernel<<<dim3(N / 128, heads, rc.B), AU_THREADS, AU_SMEM, s>>>(*amap, op, N, C, sl2, l);
+                    return cudaGetLastError();
+                }
+                if (ak) {
+                    attn_umma_kv_kernel<<<dim3(N / 128, heads, rc.B), AK_THREADS, AK_SMEM, s>>>(*amap, op, N, C, sl2, l);
                     return cudaGetLastError();
                 }
                 dim3 grid(N / 64, heads, rc.B);
