@@ -84,6 +84,27 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes of a register pair)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(r);
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

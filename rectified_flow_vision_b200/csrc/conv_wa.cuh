@@ -449,9 +449,10 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int q0 = ti * g.adv;
             const int cbase = nt * g.ctile + q * (PAIR ? 16 : 32);   // first channel of this warp
             bf16* const obase = p.out + (size_t)n * HW * p.Cout + cbase;
-            float addv[CV], s1[CV], s2[CV];
+            float addv[CV];
+            float2 s1[CV], s2[CV];   // statistics as (even column, odd column) pairs: packed fp32x2 adds / FMAs
 #pragma unroll
-            for (int v = 0; v < CV; ++v) { addv[v] = addn[v]; s1[v] = 0.f; s2[v] = 0.f; }
+            for (int v = 0; v < CV; ++v) { addv[v] = addn[v]; s1[v] = make_float2(0.f, 0.f); s2[v] = make_float2(0.f, 0.f); }
             if (tile + (int)gridDim.x < total_tiles) load_addend(tile + gridDim.x, addn);
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
@@ -487,6 +488,8 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 uint32_t mprev[2] = {0u, 0u};
 #pragma unroll
                 for (int gp = 0; gp < 2; ++gp) {
+                    // columns outside the image are SELECTED away, never multiplied by zero: their accumulators come from shared-memory
+                    // rows behind the box (whatever bytes lie there -- NaN / inf bit patterns included)
                     const bool vA = (m2 & (1u << (8 * gp))) != 0, vB = (m2 & (2u << (8 * gp))) != 0;
                     uint32_t m[4];
                     if (PAIR) {
@@ -497,11 +500,11 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             const float b0n = __uint_as_float(gp < 1 ? r[hh][4 * gp + 6] : nx[hh][2]);   // b0 of the next column group
                             const float send = t4 == 0 ? b0n : b0;
                             const float got = __shfl_sync(0xffffffffu, send, (lane & ~3) | ((lane + 1) & 3));
-                            const float oA = a0 + b1 + addv[hh], oB = a1 + got + addv[hh];
-                            const float xA = vA ? oA : 0.f, xB = vB ? oB : 0.f;
-                            s1[hh] += xA + xB;
-                            s2[hh] = fmaf(xA, xA, fmaf(xB, xB, s2[hh]));
-                            m[hh] = pack_bf16x2(oA, oB);
+                            const float2 o = fadd2(fadd2(make_float2(a0, a1), make_float2(b1, got)), make_float2(addv[hh], addv[hh]));
+                            const float2 x = make_float2(vA ? o.x : 0.f, vB ? o.y : 0.f);
+                            s1[hh] = fadd2(s1[hh], x);
+                            s2[hh] = ffma2(x, x, s2[hh]);
+                            m[hh] = pack_bf16x2(o.x, o.y);
                         }
                         // both column groups in one stmatrix: matrices {gp 0: hh0, hh1, gp 1: hh0, hh1}
                         if (gp & 1) {
@@ -514,12 +517,12 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
                             const int hh = v >> 1, k = v & 1;
-                            const float oA = __uint_as_float(r[hh][4 * gp + 2 * k]) + addv[v];
-                            const float oB = __uint_as_float(r[hh][4 * gp + 2 * k + 1]) + addv[v];
-                            const float xA = vA ? oA : 0.f, xB = vB ? oB : 0.f;
-                            s1[v] += xA + xB;
-                            s2[v] = fmaf(xA, xA, fmaf(xB, xB, s2[v]));
-                            m[v] = pack_bf16x2(oA, oB);
+                            const float2 o = fadd2(make_float2(__uint_as_float(r[hh][4 * gp + 2 * k]), __uint_as_float(r[hh][4 * gp + 2 * k + 1])),
+                                                   make_float2(addv[v], addv[v]));
+                            const float2 x = make_float2(vA ? o.x : 0.f, vB ? o.y : 0.f);
+                            s1[v] = fadd2(s1[v], x);
+                            s2[v] = ffma2(x, x, s2[v]);
+                            m[v] = pack_bf16x2(o.x, o.y);
                         }
                         const uint32_t a = stage + (uint32_t)((8 * gp + (lane & 7)) * SP + (lane >> 3) * 16);
                         stmatrix_x4_trans(a, m[0], m[1], m[2], m[3]);
@@ -543,7 +546,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 // transposing butterfly: every value is summed over all 32 lanes (4 column lanes x 8 channels of an 8-block)
                 float t[8];
 #pragma unroll
-                for (int v = 0; v < CV; ++v) { t[2 * v] = s1[v]; t[2 * v + 1] = s2[v]; }
+                for (int v = 0; v < CV; ++v) { t[2 * v] = s1[v].x + s1[v].y; t[2 * v + 1] = s2[v].x + s2[v].y; }
                 int idx;
                 if (PAIR) {
 #pragma unroll
