@@ -87,6 +87,8 @@ typedef struct {
                                     * (conv_umma.cuh) that serves every other conv shape (A/B) */
 #define RFV_FLAG_NO_GRAPH  4194304 /* Euler loops: enqueue every kernel of every step directly instead of replaying the captured
                                     * CUDA graph of the whole N-step loop of a micro-batch (A/B; profiling mode does so too) */
+#define RFV_FLAG_NO_CTA_PAIR 8388608 /* 256-output-channel stride-1 convs: one CTA per tile (conv_umma_kernel<256>) instead of CTA pairs
+                                    * executing one M = 256 tcgen05.mma.cta_group::2 (conv_umma2.cuh); A/B */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

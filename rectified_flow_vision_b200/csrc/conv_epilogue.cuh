@@ -21,7 +21,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 template <int BN>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t taddr, int n, bool n_ok, bool valid,
                                                    size_t pix, int nt, int lane, uint64_t* tfull, uint32_t parity,
-                                                   uint64_t* tempty, bool release = true) {
+                                                   uint64_t* tempty, bool release = true, bool pair = false) {
     constexpr int NCH = BN / 32;
     const bf16* rbase = p.resid ? p.resid + pix * p.Cout + (size_t)nt * BN : nullptr;
     const bool has_res = rbase != nullptr && valid;
@@ -51,7 +51,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
         tmem_ld_wait();
         if (ch == NCH - 1 && release) {  // accumulator fully in registers: hand the TMEM stage back to the MMA issuer
             tc_fence_before();
-            mbar_arrive(tempty);
+            if (pair) mbar_arrive_remote(tempty, 0);   // CTA pair: the leader's MMA issuer waits for both CTAs' epilogues
+            else mbar_arrive(tempty);
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(acc[i]);

@@ -26,6 +26,7 @@
 #include "conv_params.h"
 #include "conv_wa.cuh"
 #include "conv_umma.cuh"
+#include "conv_umma2.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
 #include "train_kernels.cuh"
@@ -580,7 +581,7 @@ struct rfv_engine {
         } else if (fr) {
             return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
         } else if (umma_ok) {
-            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; };
+            struct Bundle { CUtensorMap a0, a1, a2, a3, w; UmmaGeom g; int BN; int max_clusters; bool pair; int pair_clusters; };
             auto bd = std::make_shared<Bundle>();
             UmmaGeom& g = bd->g;
             const int bw = std::min(gW, 128), bh = std::min(gH, 128 / bw), bn = 128 / (bw * bh);
@@ -612,7 +613,26 @@ struct rfv_engine {
                                           (size_t)2 * C, (size_t)2 * Wi * C, (size_t)Hi * Wi * C, bw, bh, bn));
             }
             g.cluster = cluster;
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), BN / g.cluster));
+            // 256-output-channel stride-1 convs run on CTA pairs (conv_umma2.cuh: one M = 256 tcgen05.mma per pair, each CTA
+            // stages half of the weight slice)
+            // (not the 1x1 convs: four K chunks per tile leave them epilogue-bound, and the pair's hand-shakes cost 2-3 % there)
+            bd->pair = BN == 256 && !g.stride2 && (g.taps == 9 || g.taps == 4) && cluster == 1 && !(cfg.flags & RFV_FLAG_NO_CTA_PAIR);
+            bd->pair_clusters = 0;
+            if (bd->pair) {
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3(num_sms / 2 * 2);
+                lc.blockDim = dim3(UMMA_THREADS);
+                lc.dynamicSmemBytes = U2_SMEM_BYTES;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                int nc = 0;
+                const cudaError_t ce = cudaOccupancyMaxActiveClusters(&nc, conv_umma2_kernel, &lc);
+                if (ce != cudaSuccess || nc < 1) { cudaGetLastError(); bd->pair = false; }
+                else bd->pair_clusters = std::min(nc, num_sms / 2);
+            }
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), bd->pair ? 128 : BN / g.cluster));
             bd->max_clusters = num_sms / g.cluster;
             if (g.cluster > 1) {  // how many clusters of this kernel can be co-resident (GPC boundaries strand SMs)
                 cudaLaunchConfig_t lc{};
@@ -641,6 +661,20 @@ struct rfv_engine {
                 if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
                 UmmaGeom g = bd->g;
                 g.m_tiles = (int)(((size_t)rc.B * gHW + 127) / 128);
+                if (bd->pair) {
+                    const int pairs = ((g.m_tiles + 1) / 2) * g.n_tiles * (g.ups ? 4 : 1);
+                    cudaLaunchConfig_t lp{};
+                    lp.gridDim = dim3(std::min(pairs, bd->pair_clusters) * 2);
+                    lp.blockDim = dim3(UMMA_THREADS);
+                    lp.dynamicSmemBytes = U2_SMEM_BYTES;
+                    lp.stream = s;
+                    cudaLaunchAttribute ap[1];
+                    ap[0].id = cudaLaunchAttributeClusterDimension;
+                    ap[0].val.clusterDim.x = 2; ap[0].val.clusterDim.y = 1; ap[0].val.clusterDim.z = 1;
+                    lp.attrs = ap;
+                    lp.numAttrs = 1;
+                    return cudaLaunchKernelEx(&lp, conv_umma2_kernel, bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                }
                 const int super_tiles = ((g.m_tiles + g.cluster - 1) / g.cluster) * g.n_tiles * (g.ups ? 4 : 1);
                 cudaLaunchConfig_t lc{};
                 lc.gridDim = dim3(std::min(super_tiles, bd->max_clusters) * g.cluster);
@@ -1088,6 +1122,7 @@ struct rfv_engine {
 int rfv_engine::build() {
     const int S = cfg.image_size, mc = cfg.model_channels, nlev = cfg.num_levels, nres = cfg.num_res_blocks;
     // opt in to > 48 KB of dynamic shared memory first: the cluster-occupancy queries below depend on it
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
@@ -1614,6 +1649,7 @@ int rfv_engine::build() {
         release(a);
     }
     if (temb_cursor != sumC) return fail(RFV_ERR_STATE, "internal: time-projection layout mismatch (%d vs %d)", temb_cursor, sumC);
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
