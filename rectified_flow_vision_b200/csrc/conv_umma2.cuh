@@ -1,4 +1,5 @@
-// conv_umma_kernel<256> on a CTA PAIR (tcgen05 cta_group::2): the 256-output-channel convolutions of the 16x16 level
+// conv_umma_kernel<256 / 128> on a CTA PAIR (tcgen05 cta_group::2): the 256-output-channel convolutions of the 16x16 level
+// and the 128-channel sub-pixel upsample conv
 // (3x3 stride 1, also as the four sub-pixel phases of an upsample conv; models/unet.py:38,41,51,217 at the lowest resolution).
 //
 // Why: with one CTA per tile every (tap, 64-channel chunk) stage moves a 16 KB pixel box AND a 32 KB weight slice into
@@ -26,16 +27,22 @@
 
 namespace rfv {
 
-constexpr int U2_BN = 256;
-constexpr int U2_B_BYTES = (U2_BN / 2) * 128;                // this CTA's half of the weight slice
-constexpr int U2_STAGE_BYTES = UMMA_A_BYTES + U2_B_BYTES;    // 32 KB
-constexpr int U2_STAGES = 6;
-constexpr int U2_SMEM_BYTES = U2_STAGES * U2_STAGE_BYTES + 1024 + 256;
+template <int BN>
+struct PairCfg {
+    static constexpr int B_BYTES = (BN / 2) * 128;                  // this CTA's half of the weight slice
+    static constexpr int STAGE_BYTES = UMMA_A_BYTES + B_BYTES;      // 32 KB (BN = 256) / 24 KB (BN = 128)
+    static constexpr int STAGES = BN == 256 ? 6 : 8;
+    static constexpr int TMEM_COLS = 2 * BN;                        // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
+template <int U2_BN>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW, const ConvParams p,
                   const UmmaGeom g) {
+    constexpr int U2_B_BYTES = PairCfg<U2_BN>::B_BYTES, U2_STAGE_BYTES = PairCfg<U2_BN>::STAGE_BYTES, U2_STAGES = PairCfg<U2_BN>::STAGES;
+    constexpr int U2_TMEM = PairCfg<U2_BN>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -58,7 +65,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 256); }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    if (warp == 2) tmem_alloc_pair(tmem_slot, U2_TMEM);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // the peer's barriers exist before anything is signalled into them
@@ -173,7 +180,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // nobody exits while the peer may still signal into, or read operands from, its shared memory
-    if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+    if (warp == 2) tmem_dealloc_pair(tmem_base, U2_TMEM);
 }
 
 }  // namespace rfv

@@ -616,23 +616,24 @@ struct rfv_engine {
             // 256-output-channel stride-1 convs run on CTA pairs (conv_umma2.cuh: one M = 256 tcgen05.mma per pair, each CTA
             // stages half of the weight slice)
             // (not the 1x1 convs: four K chunks per tile leave them epilogue-bound, and the pair's hand-shakes cost 2-3 % there)
-            bd->pair = BN == 256 && !g.stride2 && (g.taps == 9 || g.taps == 4) && cluster == 1 && !(cfg.flags & RFV_FLAG_NO_CTA_PAIR);
+            bd->pair = (BN == 256 || BN == 128) && !g.stride2 && (g.taps == 9 || g.taps == 4) && cluster == 1 && !(cfg.flags & RFV_FLAG_NO_CTA_PAIR);
             bd->pair_clusters = 0;
             if (bd->pair) {
                 cudaLaunchConfig_t lc{};
                 lc.gridDim = dim3(num_sms / 2 * 2);
                 lc.blockDim = dim3(UMMA_THREADS);
-                lc.dynamicSmemBytes = U2_SMEM_BYTES;
+                lc.dynamicSmemBytes = BN == 256 ? PairCfg<256>::SMEM_BYTES : PairCfg<128>::SMEM_BYTES;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 lc.attrs = at; lc.numAttrs = 1;
                 int nc = 0;
-                const cudaError_t ce = cudaOccupancyMaxActiveClusters(&nc, conv_umma2_kernel, &lc);
+                const cudaError_t ce = BN == 256 ? cudaOccupancyMaxActiveClusters(&nc, conv_umma2_kernel<256>, &lc)
+                                                 : cudaOccupancyMaxActiveClusters(&nc, conv_umma2_kernel<128>, &lc);
                 if (ce != cudaSuccess || nc < 1) { cudaGetLastError(); bd->pair = false; }
                 else bd->pair_clusters = std::min(nc, num_sms / 2);
             }
-            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), bd->pair ? 128 : BN / g.cluster));
+            RFV_TRY(make_map2(&bd->w, L->w, L->Ktot, L->Cout * (L->subpixel ? 4 : 1), bd->pair ? BN / 2 : BN / g.cluster));
             bd->max_clusters = num_sms / g.cluster;
             if (g.cluster > 1) {  // how many clusters of this kernel can be co-resident (GPC boundaries strand SMs)
                 cudaLaunchConfig_t lc{};
@@ -666,14 +667,18 @@ struct rfv_engine {
                     cudaLaunchConfig_t lp{};
                     lp.gridDim = dim3(std::min(pairs, bd->pair_clusters) * 2);
                     lp.blockDim = dim3(UMMA_THREADS);
-                    lp.dynamicSmemBytes = U2_SMEM_BYTES;
                     lp.stream = s;
                     cudaLaunchAttribute ap[1];
                     ap[0].id = cudaLaunchAttributeClusterDimension;
                     ap[0].val.clusterDim.x = 2; ap[0].val.clusterDim.y = 1; ap[0].val.clusterDim.z = 1;
                     lp.attrs = ap;
                     lp.numAttrs = 1;
-                    return cudaLaunchKernelEx(&lp, conv_umma2_kernel, bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                    if (bd->BN == 256) {
+                        lp.dynamicSmemBytes = PairCfg<256>::SMEM_BYTES;
+                        return cudaLaunchKernelEx(&lp, conv_umma2_kernel<256>, bd->a0, bd->a1, bd->a2, bd->w, q, g);
+                    }
+                    lp.dynamicSmemBytes = PairCfg<128>::SMEM_BYTES;
+                    return cudaLaunchKernelEx(&lp, conv_umma2_kernel<128>, bd->a0, bd->a1, bd->a2, bd->w, q, g);
                 }
                 const int super_tiles = ((g.m_tiles + g.cluster - 1) / g.cluster) * g.n_tiles * (g.ups ? 4 : 1);
                 cudaLaunchConfig_t lc{};
@@ -1122,7 +1127,8 @@ struct rfv_engine {
 int rfv_engine::build() {
     const int S = cfg.image_size, mc = cfg.model_channels, nlev = cfg.num_levels, nres = cfg.num_res_blocks;
     // opt in to > 48 KB of dynamic shared memory first: the cluster-occupancy queries below depend on it
-    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
@@ -1649,7 +1655,8 @@ int rfv_engine::build() {
         release(a);
     }
     if (temb_cursor != sumC) return fail(RFV_ERR_STATE, "internal: time-projection layout mismatch (%d vs %d)", temb_cursor, sumC);
-    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::SMEM_BYTES));
+    CU_CHECK(cudaFuncSetAttribute(conv_umma2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128>::SMEM_BYTES));
     CU_CHECK(cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64>::SMEM_BYTES));
