@@ -154,6 +154,32 @@ def test_loop_graph_replay_matches_direct_launches():
     assert util.rel_l2(traj[1].cpu().numpy(), a.cpu().numpy()) < 2e-2
 
 
+def test_cta_pair_kernel_with_an_odd_number_of_tiles():
+    """conv_umma2.cuh: a CTA pair takes m-tiles 2g and 2g+1; with an odd tile count the last pair's second CTA runs a tile past
+    the end (zero-filled boxes, nothing stored, no statistics).  32-pixel three-level net: the 256-channel level is 8x8 = 64
+    pixels per image, so 5 images are 2.5 -> 3 tiles.  Against the single-CTA kernel and against the CPU oracle."""
+    import rectified_flow_vision_b200 as pkg
+    from oracle import unet_oracle as O
+    from rectified_flow_vision_b200 import engine as E
+    torch.manual_seed(11)
+    kw = dict(image_size=32, model_channels=64, channel_mult=[1, 2, 4], num_res_blocks=1)
+    m = pkg.BaseFlowModel(device="cuda:0", **kw)
+    gen = torch.Generator().manual_seed(12)
+    spec = O.UNetSpec(model_channels=64, channel_mult=(1, 2, 4), num_res_blocks=1)
+    P = util.numpy_params(m)
+    for rows in (5, 1, 2):
+        x, t = torch.randn(rows, 3, 32, 32, generator=gen), torch.rand(rows, generator=gen)
+        outs = []
+        for fl in (0, 8388608):
+            eng = E.Engine(m.velocity_net.arch(), 32, torch.device("cuda:0"), micro_batch=8, flags=fl)
+            eng.sync_weights(m.velocity_net)
+            outs.append(eng.velocity(x.cuda(), t.cuda()).cpu().numpy())
+        ref = O.unet_forward(P, x.numpy(), t.numpy(), spec)
+        assert np.isfinite(outs[0]).all()
+        assert util.rel_l2(outs[0], outs[1]) <= 2e-2, rows
+        assert util.rel_l2(outs[0], ref) <= 3e-2 and util.max_rel(outs[0], ref) <= 5e-2, rows
+
+
 NO_WA = 1048576   # RFV_FLAG_NO_WA: per-tap implicit-GEMM kernel instead of the weights-as-A kernel
 
 
@@ -161,7 +187,8 @@ NO_WA = 1048576   # RFV_FLAG_NO_WA: per-tap implicit-GEMM kernel instead of the 
                                        (4096, "GroupNorm fused into every weights-as-A conv"), (512, "cluster-2 weight multicast"),
                                        (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"),
                                        (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"), (524288, "no GroupNorm fusion"),
-                                       (1, "mma.sync implicit-GEMM convs (no tcgen05)")])
+                                       (1, "mma.sync implicit-GEMM convs (no tcgen05)"), (8388608, "single-CTA 256-channel convs (no CTA pairs)"),
+                                       (4194304, "no loop graphs")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
     """The A/B kernels kept behind RFV_FLAG_* (include/rfv.h) compute the same velocity as the default plan."""
     from rectified_flow_vision_b200 import engine as E

@@ -54,7 +54,7 @@ def test_velocity_on_perturbed_weights(case):
 
 @pytest.mark.parametrize("flags,name", [(0, "default plan"), (FLAG_FUSE_GN, "GroupNorm fused into every weights-as-A conv"),
                                         (FLAG_NO_FUSE_GN, "GroupNorm never fused"), (FLAG_NO_WA, "per-tap tcgen05 kernel"),
-                                        (FLAG_NO_UMMA, "mma.sync kernels")])
+                                        (FLAG_NO_UMMA, "mma.sync kernels"), (8388608, "single-CTA 256-channel convs (no CTA pairs)")])
 def test_every_kernel_plan_on_perturbed_weights(flags, name):
     """gamma / beta indexing of each GroupNorm code path (stand-alone apply, coefficient table of the fused conv, virtual
     concat) checked where it is visible: on weights with gamma != 1, beta != 0."""
