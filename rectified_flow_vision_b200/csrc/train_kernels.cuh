@@ -89,6 +89,33 @@ __device__ __forceinline__ float sigmoid_fast(float z) {
     return fmaf(0.5f, t, 0.5f);
 }
 
+// The element-wise cores below work on (even, odd) channel PAIRS with the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 /
+// FFMA2: one issue slot for two elements) -- these kernels are issue-bound, and the FP32 arithmetic was half of their
+// instruction stream.  dz[p] *= silu'(z), z = x*sc + sh, silu'(z) = sg * (1 + z * (1 - sg)), sg = sigmoid(z) via one tanh each.
+__device__ __forceinline__ void unpack8p(const uint4& q, float2* f) {
+    f[0] = unpack_bf16x2(q.x); f[1] = unpack_bf16x2(q.y); f[2] = unpack_bf16x2(q.z); f[3] = unpack_bf16x2(q.w);
+}
+__device__ __forceinline__ uint4 pack8p(const float2* f) {
+    uint4 q;
+    q.x = pack_bf16x2(f[0].x, f[0].y); q.y = pack_bf16x2(f[1].x, f[1].y);
+    q.z = pack_bf16x2(f[2].x, f[2].y); q.w = pack_bf16x2(f[3].x, f[3].y);
+    return q;
+}
+__device__ __forceinline__ void silu_grad4(float2* dz, const float2* x, const float2* sc, const float2* sh) {
+    const float2 half = make_float2(0.5f, 0.5f), one = make_float2(1.f, 1.f), neg = make_float2(-1.f, -1.f);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 z = ffma2(x[p], sc[p], sh[p]);
+        const float2 zh = fmul2(z, half);
+        float2 t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(zh.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(zh.y));
+        const float2 sg = ffma2(half, t, half);
+        const float2 q = ffma2(z, ffma2(sg, neg, one), one);
+        dz[p] = fmul2(dz[p], fmul2(sg, q));
+    }
+}
+
 // Arithmetic is arranged so that the per-element work is a handful of FMAs (these kernels are issue-bound, not HBM-bound,
 // when written naively):  z = x*sc + sh;  silu'(z) = sg + z*(sg - sg^2);  pass 1 accumulates sum(dz) and sum(dz*x) and
 // converts to sum(dz*xhat) at the end;  pass 2 is dx = dz*k1[c] + x*k2 + k3 with per-group constants k2, k3.
@@ -123,11 +150,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
     const int grp = (cv * 8) / cpg;
     const float mean = gmean[grp], rstd = grstd[grp];
-    float sc[8], sh[8];   // z = x*sc + sh with sc = rstd*gamma (also the dz coefficient of dx)
+    float2 sc[4], sh[4];   // z = x*sc + sh with sc = rstd*gamma (also the dz coefficient of dx); (even, odd) channel pairs
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = rstd * a.gamma[cv * 8 + j];
-        sh[j] = a.beta[cv * 8 + j] - mean * sc[j];
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = make_float2(rstd * a.gamma[cv * 8 + 2 * j], rstd * a.gamma[cv * 8 + 2 * j + 1]);
+        sh[j] = make_float2(a.beta[cv * 8 + 2 * j] - mean * sc[j].x, a.beta[cv * 8 + 2 * j + 1] - mean * sc[j].y);
     }
     const bool from_a = cv * 8 < a.Ca;
     const bf16* src = from_a ? a.xa + cv * 8 : a.xb + (cv * 8 - a.Ca);
@@ -137,11 +164,12 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     const int p0 = blockIdx.x * a.pix_per_block;
     const int np = min(a.pix_per_block, a.HW - p0);
     const size_t base = (size_t)n * a.HW + p0;
-    float accA[8], accB[8];
+    float2 accA[4], accB[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { accA[j] = make_float2(0.f, 0.f); accB[j] = make_float2(0.f, 0.f); }
     const float s1 = APPLY ? gS1[grp] : 0.f, s2 = APPLY ? gS2[grp] : 0.f;
-    const float k2 = -rstd * rstd * s2, k3 = -rstd * s1 - mean * k2;   // dx = dz*sc + x*k2 + k3
+    const float k2s = -rstd * rstd * s2, k3s = -rstd * s1 - mean * k2s;   // dx = dz*sc + x*k2 + k3
+    const float2 k2 = make_float2(k2s, k2s), k3 = make_float2(k3s, k3s);
     const bool has_cat = APPLY && a.add_cat != nullptr, has_a = APPLY && a.add_a != nullptr && from_a;
     constexpr int U = 2;
     for (int pp = pl; pp < np; pp += U * pstride) {
@@ -161,54 +189,56 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
         for (int u = 0; u < U; ++u) {
             const int px = pp + u * pstride;
             if (px >= np) continue;
-            float x[8], d[8], mk[8];
-            unpack8(qx[u], x);
-            unpack8(qd[u], d);
-            if (a.drop_thresh) dropout_mask8(a.seed, (uint32_t)((base + px) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
-            float r[8];
+            float2 x[4], dz[4];
+            unpack8p(qx[u], x);
+            unpack8p(qd[u], dz);
+            if (a.drop_thresh) {
+                float mk[8];
+                dropout_mask8(a.seed, (uint32_t)((base + px) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float dz = a.drop_thresh ? d[j] * mk[j] : d[j];
-                if (a.silu) {
-                    const float z = fmaf(x[j], sc[j], sh[j]);
-                    const float sg = sigmoid_fast(z);
-                    dz *= fmaf(z, fmaf(-sg, sg, sg), sg);
-                }
-                if (APPLY) r[j] = fmaf(dz, sc[j], fmaf(x[j], k2, k3));
-                else { accA[j] += dz; accB[j] = fmaf(dz, x[j], accB[j]); }
+                for (int j = 0; j < 4; ++j) dz[j] = fmul2(dz[j], make_float2(mk[2 * j], mk[2 * j + 1]));
             }
-            if (APPLY) {
-                float f[8];
-                if (has_cat) {
-                    unpack8(qc[u], f);
+            if (a.silu) silu_grad4(dz, x, sc, sh);
+            if (!APPLY) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                for (int j = 0; j < 4; ++j) { accA[j] = fadd2(accA[j], dz[j]); accB[j] = ffma2(dz[j], x[j], accB[j]); }
+            } else {
+                float2 r[4], f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = ffma2(dz[j], sc[j], ffma2(x[j], k2, k3));
+                if (has_cat) {
+                    unpack8p(qc[u], f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
                 }
                 if (has_a) {
-                    unpack8(qa[u], f);
+                    unpack8p(qa[u], f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                    for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
                 }
                 if (acc) {
-                    unpack8(qo[u], f);
+                    unpack8p(qo[u], f);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] += f[j];
+                    for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
                 }
                 if (a.out_colsum) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) accA[j] += r[j];
+                    for (int j = 0; j < 4; ++j) accA[j] = fadd2(accA[j], r[j]);
                 }
-                *reinterpret_cast<uint4*>(dst + (base + px) * cs_) = pack8(r);
+                *reinterpret_cast<uint4*>(dst + (base + px) * cs_) = pack8p(r);
             }
         }
     }
+    float fA[8], fB[8];   // the pair accumulators as per-channel scalars for the reductions
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { fA[2 * j] = accA[j].x; fA[2 * j + 1] = accA[j].y; fB[2 * j] = accB[j].x; fB[2 * j + 1] = accB[j].y; }
     if (!APPLY) {
-        const bool pub_a = warp_sum_same_cv<8>(accA, vpp), pub_b = warp_sum_same_cv<8>(accB, vpp);
+        const bool pub_a = warp_sum_same_cv<8>(fA, vpp), pub_b = warp_sum_same_cv<8>(fB, vpp);
         if (pub_a && pub_b) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                atomicAdd(&sm[(cv * 8 + j) * 2], accA[j]);
-                atomicAdd(&sm[(cv * 8 + j) * 2 + 1], rstd * (accB[j] - mean * accA[j]));   // sum dz*xhat
+                atomicAdd(&sm[(cv * 8 + j) * 2], fA[j]);
+                atomicAdd(&sm[(cv * 8 + j) * 2 + 1], rstd * (fB[j] - mean * fA[j]));   // sum dz*xhat
             }
         }
         __syncthreads();
@@ -216,9 +246,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_kernel(const GnBwdArgs a) {
     } else if (a.out_colsum) {   // dynamic shared memory [C] (the launcher sizes it)
         for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
         __syncthreads();
-        if (warp_sum_same_cv<8>(accA, vpp)) {
+        if (warp_sum_same_cv<8>(fA, vpp)) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], accA[j]);
+            for (int j = 0; j < 8; ++j) atomicAdd(&sm[cv * 8 + j], fA[j]);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < a.Ca; i += blockDim.x) atomicAdd(a.out_colsum + (size_t)n * a.ld_colsum + i, sm[i]);
@@ -289,51 +319,47 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const GnBwdArgs a,
     const int vpp = C >> 3, cv = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = blockDim.x / vpp;
     const int grp = (cv * 8) / cpg;
     const float mean = gmean[grp], rstd = grstd[grp];
-    float sc[8], sh[8];
+    float2 sc[4], sh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = rstd * a.gamma[cv * 8 + j];
-        sh[j] = a.beta[cv * 8 + j] - mean * sc[j];
+    for (int j = 0; j < 4; ++j) {
+        sc[j] = make_float2(rstd * a.gamma[cv * 8 + 2 * j], rstd * a.gamma[cv * 8 + 2 * j + 1]);
+        sh[j] = make_float2(a.beta[cv * 8 + 2 * j] - mean * sc[j].x, a.beta[cv * 8 + 2 * j + 1] - mean * sc[j].y);
     }
     const bool from_a = cv * 8 < a.Ca;
     const bf16* xs = from_a ? xsa + cv * 8 : xsb + (cv * 8 - a.Ca);
     const int cs_ = from_a ? a.Ca : a.Cb;
-    float accA[8], accB[8];
+    float2 accA[4], accB[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { accA[j] = make_float2(0.f, 0.f); accB[j] = make_float2(0.f, 0.f); }
     for (int s = 0; s < GNF_STAGES; ++s) {
         mbar_wait(&bars[s], 0);
         for (int pp = s * ps + pl; pp < (s + 1) * ps; pp += pstride) {
-            float x[8], dz[8];
+            float2 x[4], dz[4];
             uint4* dzp = reinterpret_cast<uint4*>(dys + (size_t)pp * C + cv * 8);
-            unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
-            unpack8(*dzp, dz);
+            unpack8p(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
+            unpack8p(*dzp, dz);
             if (a.drop_thresh) {
                 float mk[8];
                 dropout_mask8(a.seed, (uint32_t)((base + pp) * C + cv * 8), a.drop_thresh, a.drop_scale, mk);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dz[j] *= mk[j];
+                for (int j = 0; j < 4; ++j) dz[j] = fmul2(dz[j], make_float2(mk[2 * j], mk[2 * j + 1]));
             }
-            if (a.silu) {
+            if (a.silu) silu_grad4(dz, x, sc, sh);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float z = fmaf(x[j], sc[j], sh[j]);
-                    const float sg = sigmoid_fast(z);
-                    dz[j] *= fmaf(z, fmaf(-sg, sg, sg), sg);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { accA[j] += dz[j]; accB[j] = fmaf(dz[j], x[j], accB[j]); }
-            if (a.drop_thresh || a.silu) *dzp = pack8(dz);   // pass 2 reads dz, not dy
+            for (int j = 0; j < 4; ++j) { accA[j] = fadd2(accA[j], dz[j]); accB[j] = ffma2(dz[j], x[j], accB[j]); }
+            if (a.drop_thresh || a.silu) *dzp = pack8p(dz);   // pass 2 reads dz, not dy
         }
     }
     {
-        const bool pub_a = warp_sum_same_cv<8>(accA, vpp), pub_b = warp_sum_same_cv<8>(accB, vpp);
+        float fA[8], fB[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { fA[2 * j] = accA[j].x; fA[2 * j + 1] = accA[j].y; fB[2 * j] = accB[j].x; fB[2 * j + 1] = accB[j].y; }
+        const bool pub_a = warp_sum_same_cv<8>(fA, vpp), pub_b = warp_sum_same_cv<8>(fB, vpp);
         if (pub_a && pub_b) {
             float* dstp = red + (size_t)(rows > 1 ? threadIdx.x >> 5 : 0) * 2 * C + cv * 16;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float va = accA[j], vb = rstd * (accB[j] - mean * accA[j]);   // sum dz, sum dz*xhat
+                const float va = fA[j], vb = rstd * (fB[j] - mean * fA[j]);   // sum dz, sum dz*xhat
                 if (rows > 1) { dstp[j * 2] = va; dstp[j * 2 + 1] = vb; }
                 else { atomicAdd(dstp + j * 2, va); atomicAdd(dstp + j * 2 + 1, vb); }
             }
@@ -378,50 +404,54 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(const GnBwdArgs a,
             atomicAdd(a.dgamma + c, tot[c * 2 + 1]);
         }
     __syncthreads();
-    const float k2 = -rstd * rstd * gS2[grp], k3 = -rstd * gS1[grp] - mean * k2;   // dx = dz*sc + x*k2 + k3
+    const float k2s = -rstd * rstd * gS2[grp], k3s = -rstd * gS1[grp] - mean * k2s;   // dx = dz*sc + x*k2 + k3
+    const float2 k2 = make_float2(k2s, k2s), k3 = make_float2(k3s, k3s);
     bf16* dst = from_a ? a.out_a + cv * 8 : a.out_b + (cv * 8 - a.Ca);
     const bool acc = from_a ? a.acc_a != 0 : a.acc_b != 0;
     const bool has_cat = a.add_cat != nullptr, has_a = a.add_a != nullptr && from_a;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) accA[j] = 0.f;
+    for (int j = 0; j < 4; ++j) accA[j] = make_float2(0.f, 0.f);
     for (int pp = pl; pp < np; pp += pstride) {
         uint4 qc, qa, qo;   // optional addends straight from global memory, issued before the arithmetic
         if (has_cat) qc = *reinterpret_cast<const uint4*>(a.add_cat + (base + pp) * C + cv * 8);
         if (has_a) qa = *reinterpret_cast<const uint4*>(a.add_a + (base + pp) * a.Ca + cv * 8);
         if (acc) qo = *reinterpret_cast<const uint4*>(dst + (base + pp) * cs_);
-        float x[8], dz[8], r[8], f[8];
-        unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
-        unpack8(*reinterpret_cast<const uint4*>(dys + (size_t)pp * C + cv * 8), dz);
+        float2 x[4], dz[4], r[4], f[4];
+        unpack8p(*reinterpret_cast<const uint4*>(xs + (size_t)pp * cs_), x);
+        unpack8p(*reinterpret_cast<const uint4*>(dys + (size_t)pp * C + cv * 8), dz);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(dz[j], sc[j], fmaf(x[j], k2, k3));
+        for (int j = 0; j < 4; ++j) r[j] = ffma2(dz[j], sc[j], ffma2(x[j], k2, k3));
         if (has_cat) {
-            unpack8(qc, f);
+            unpack8p(qc, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += f[j];
+            for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
         }
         if (has_a) {
-            unpack8(qa, f);
+            unpack8p(qa, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += f[j];
+            for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
         }
         if (acc) {
-            unpack8(qo, f);
+            unpack8p(qo, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] += f[j];
+            for (int j = 0; j < 4; ++j) r[j] = fadd2(r[j], f[j]);
         }
         if (a.out_colsum) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) accA[j] += r[j];
+            for (int j = 0; j < 4; ++j) accA[j] = fadd2(accA[j], r[j]);
         }
-        *reinterpret_cast<uint4*>(dst + (base + pp) * cs_) = pack8(r);
+        *reinterpret_cast<uint4*>(dst + (base + pp) * cs_) = pack8p(r);
     }
     if (a.out_colsum) {
         __syncthreads();
         for (int i = threadIdx.x; i < C; i += blockDim.x) tot[i] = 0.f;
         __syncthreads();
-        if (warp_sum_same_cv<8>(accA, vpp)) {
+        float fA[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(&tot[cv * 8 + j], accA[j]);
+        for (int j = 0; j < 4; ++j) { fA[2 * j] = accA[j].x; fA[2 * j + 1] = accA[j].y; }
+        if (warp_sum_same_cv<8>(fA, vpp)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&tot[cv * 8 + j], fA[j]);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < a.Ca; i += blockDim.x) atomicAdd(a.out_colsum + (size_t)n * a.ld_colsum + i, tot[i]);
