@@ -89,6 +89,10 @@ typedef struct {
                                     * CUDA graph of the whole N-step loop of a micro-batch (A/B; profiling mode does so too) */
 #define RFV_FLAG_NO_CTA_PAIR 8388608 /* 256-output-channel stride-1 convs: one CTA per tile (conv_umma_kernel<256>) instead of CTA pairs
                                     * executing one M = 256 tcgen05.mma.cta_group::2 (conv_umma2.cuh); A/B */
+#define RFV_FLAG_NO_PDL    16777216 /* sampling chains: launch every kernel fully serialised behind its predecessor instead of as a
+                                    * programmatic dependent (cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's
+                                    * prologue -- barrier init, TMEM allocation, resident weight loads -- runs under the tail of the
+                                    * previous one and stops in griddepcontrol.wait); A/B */
 #define RFV_FLAG_TRAIN     32  /* build the backward plan too: keeps every activation, allocates gradient / Adam buffers */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */

@@ -12,6 +12,8 @@ namespace rfv {
 template <int D>  // head dim: 32, 64 or 128
 __global__ void __launch_bounds__(128) attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, int C,
                                                    float scale_log2, float* __restrict__ lse) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     constexpr int ATT_LD = D + 8;  // padded row length (bf16) -> conflict-free ldmatrix
     constexpr int KS = D / 16;     // k16 steps over the head dim
     __shared__ __align__(16) bf16 Qs[64][ATT_LD];

@@ -44,6 +44,8 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQKV, bf16* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();   // programmatic dependent launch (common.cuh)
+    if (threadIdx.x == 0) pdl_launch();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -180,6 +182,8 @@ attn_umma_kv_kernel(const __grid_constant__ CUtensorMap mapQKV, bf16* __restrict
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();   // programmatic dependent launch (common.cuh)
+    if (threadIdx.x == 0) pdl_launch();
     const uint32_t tmem_o = tmem + 256;
 
     if (warp == 0) {

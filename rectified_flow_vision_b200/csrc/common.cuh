@@ -154,6 +154,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while the kernel before it in the stream (or its predecessor node of a captured graph) is still running: its CTAs take the
+// SMs the predecessor's last CTAs leave, run their prologue (barrier init, TMEM allocation, descriptor prefetch, resident
+// weight loads) and stop in pdl_wait() until the predecessor has COMPLETED and its writes are visible.  Every thread that
+// reads or writes global memory a neighbouring kernel touches waits first; pdl_launch() (after the wait: at most two kernels
+// overlap) lets the successor do the same.  Without the launch attribute both are no-ops.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tiled mode, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {

@@ -10,6 +10,8 @@ namespace rfv {
 constexpr int MMA_BM = 128, MMA_BN = 64, MMA_BK = 32, MMA_STAGES = 3, MMA_LD = 40;
 
 __global__ void __launch_bounds__(256) conv_mma_kernel(const ConvParams p) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     __shared__ __align__(16) bf16 As[MMA_STAGES][MMA_BM][MMA_LD];
     __shared__ __align__(16) bf16 Bs[MMA_STAGES][MMA_BN][MMA_LD];
 

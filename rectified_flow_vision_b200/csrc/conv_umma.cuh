@@ -87,6 +87,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (CL > 1) cluster_sync_all();  // peers' barriers must be initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp != 1) pdl_wait();   // programmatic dependent launch (common.cuh): everything above overlapped the predecessor's tail
+    if (threadIdx.x == 0) pdl_launch();
 
     const int nkb0 = g.taps * g.cch0;
     const int nkb = nkb0 + g.cch1a + g.cch1b;

@@ -71,6 +71,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     cluster_sync_all();   // the peer's barriers exist before anything is signalled into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp != 1) pdl_wait();   // programmatic dependent launch (common.cuh): everything above overlapped the predecessor's tail
+    if (threadIdx.x == 0) pdl_launch();
 
     const int nkb0 = g.taps * g.cch0;
     const int nkb = nkb0 + g.cch1a + g.cch1b;

@@ -56,6 +56,11 @@ struct WaGeom {
     int pf;                       // L2 prefetch distance in tiles (0 = off)
     int rs;                       // box rows per TMA request (a box is fetched as ceil(rows / rs) requests: one request streams at
                                   // only ~12 B/clk, several in flight overlap)
+    int tblk;                     // resident weight blocks held in TENSOR MEMORY (the first tblk blocks of a tile's sequence, all in chunk 0;
+                                  // 32 columns each at column tcol0 + 32 b) and multiplied in TS mode (A operand from TMEM); the rest
+                                  // of the resident blocks stay in shared memory.  0 = off.
+    int tcol0;
+    const void* wa;               // the packed weight blocks in global memory (the TMEM preload reads them directly)
     int dbg;                      // experiments (RFV_WA_DBG): 1 = epilogue only waits / releases, 2 = no MMAs issued, 4 = no global stores,
                                   // 8 = no TMA loads (barriers only)
 };
@@ -77,6 +82,8 @@ __host__ __device__ constexpr int wa_staging_bytes(bool pair, bool fuse) { retur
 __global__ void __launch_bounds__(256) gn_coef_kernel(const float* __restrict__ stats_a, const float* __restrict__ stats_b,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float* __restrict__ coef, int Ca, int Cb, int HW, int slab_shift, float eps) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     __shared__ float gmean[8], grstd[8];
     const int C = Ca + Cb, n = blockIdx.x, cpg = C / 8;
     if (threadIdx.x < 8) {
@@ -154,9 +161,46 @@ __device__ __forceinline__ void tmem_ld_16x256_x1(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr)
                  : "memory");
 }
+// one 32-lane x 32-column slab of tensor memory from registers: thread = lane (row), register j = 32-bit column j
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+        ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+          "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+          "r"(r[31]), "r"(taddr)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (128 rows = lanes, K = 16 bf16 = 8 columns per instruction) comes from
+// tensor memory (tools/micro/ts_mma_test.cu: layout and results verified; same rate as the shared-memory form at N >= 164)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
                  : "memory");
+}
+
+// (not inlined: its 32 staging registers must not count against the epilogue's register budget)
+__device__ __noinline__ void wa_preload_tmem(const void* wa, int tblk, uint32_t taddr, int row) {
+    for (int b = 0; b < tblk; ++b) {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const bf16*>(wa) + ((size_t)b * 128 + row) * 64);
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 t = __ldg(src + i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+        tmem_st_32x32(taddr + (uint32_t)(32 * b), v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 template <bool PAIR, bool FUSE>
@@ -171,7 +215,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint8_t* smem_w = smem_x + (size_t)g.a_stages * g.stage_bytes;
     const int nchunks = g.cch0 + g.cch1a + g.cch1b + g.cchr;
     const int nblk_used = g.cch0 * g.slots0 + g.cch1a + g.cch1b + g.cchr;
-    const int w_slots = g.resident ? nblk_used : g.w_stages;
+    const int w_slots = g.resident ? nblk_used - g.tblk : g.w_stages;
     uint8_t* smem_o = smem_w + (size_t)w_slots * WA_BLK;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + wa_staging_bytes(PAIR, FUSE));
     uint64_t* xfull = bars;                       // TMA -> (transform | MMA)
@@ -203,6 +247,21 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int total_tiles = g.m_tiles * g.n_tiles;
+    if (g.tblk > 0) {
+        // weight blocks that live in tensor memory for the whole launch: warp 4 + q writes rows 32 q .. 32 q + 31 (its lane
+        // quarter), thread = row, 32 registers = the row's 64 bf16 (column j = K elements 2j, 2j+1).  Weights are constant
+        // while a sampling chain runs, so this precedes pdl_wait like the resident shared-memory blocks.
+        if (warp >= 4 && warp < 8) wa_preload_tmem(g.wa, g.tblk, tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g.tcol0, (warp & 3) * 32 + lane);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    // programmatic dependent launch: the box producer, the transform and the epilogue warps touch activations / statistics /
+    // coefficients of neighbouring kernels and wait for the predecessor here; the weight producer (weights are constant
+    // while a sampling chain runs) and the MMA warp (no global accesses) go ahead, so the resident weight blocks land under
+    // the predecessor's tail
+    if (warp != 1 && warp != 3) pdl_wait();
+    if (threadIdx.x == 0) pdl_launch();
 
     if (warp < 4) {
         if (FUSE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
@@ -231,7 +290,8 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             else if ((c -= g.cch0) < g.cch1a) mp = &mapA1;
                             else if ((c -= g.cch1a) < g.cch1b) mp = &mapA2;
                             else { mp = &mapR; c = ntp * (g.ctile / 64) + (c - g.cch1b); }
-                            for (int r0 = 0; r0 < g.rows; r0 += g.rs) tma_prefetch_4d(mp, c * 64, -1, rbp + r0, np);
+                            const int trim = (ch >= g.cch0 && g.rs == 1) ? 1 : 0;   // centre-only chunks: see the loads below
+                            for (int r0 = trim; r0 < g.rows - trim; r0 += g.rs) tma_prefetch_4d(mp, c * 64, -1, rbp + r0, np);
                         }
                     }
                     __syncwarp();
@@ -240,7 +300,11 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     mbar_wait(&xempty[st], ph ^ 1);
                     if (g.dbg & 8) { if (elect_one()) mbar_arrive(&xfull[st]); }
                     else if (elect_one()) {
-                        mbar_arrive_expect_tx(&xfull[st], g.box_bytes);
+                        // shortcut / residual chunks are multiplied at the centre shift only: their MMAs read box rows
+                        // 1 .. rows-2 (idx0 lies in [pitch, 2 pitch), idx0 + N - 1 < (rows - 1) pitch), so the two halo rows are
+                        // not fetched (these layers are bound by the box loads: two to four boxes per tile at ~24 B/clk per SM)
+                        const int trim = (ch >= g.cch0 && g.rs == 1) ? 1 : 0;
+                        mbar_arrive_expect_tx(&xfull[st], g.box_bytes - 2 * trim * g.pitch * 128);
                         uint8_t* dst = smem_x + (size_t)st * g.stage_bytes;
                         int c = ch;
                         const CUtensorMap* mp;
@@ -249,7 +313,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         else if ((c -= g.cch0) < g.cch1a) mp = &mapA1;
                         else if ((c -= g.cch1a) < g.cch1b) mp = &mapA2;
                         else { mp = &mapR; c = nt * (g.ctile / 64) + (c - g.cch1b); }
-                        for (int r0 = 0; r0 < g.rows; r0 += g.rs)
+                        for (int r0 = trim; r0 < g.rows - trim; r0 += g.rs)
                             tma_load_4d(dst + (size_t)r0 * g.pitch * 128, mp, &xfull[st], c * 64, -1, rbox + r0, n);
                     }
                     __syncwarp();
@@ -259,9 +323,9 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         } else if (warp == 3) {
             // ===================== weight producer: 16 KB blocks in consumption order =====================
             if (g.resident) {
-                if ((int)blockIdx.x < total_tiles && elect_one()) {
-                    mbar_arrive_expect_tx(&wfull[0], nblk_used * WA_BLK);
-                    for (int b = 0; b < nblk_used; ++b) tma_load_2d(smem_w + (size_t)b * WA_BLK, &mapW, &wfull[0], 0, b * 128);
+                if ((int)blockIdx.x < total_tiles && nblk_used > g.tblk && elect_one()) {
+                    mbar_arrive_expect_tx(&wfull[0], (nblk_used - g.tblk) * WA_BLK);
+                    for (int b = g.tblk; b < nblk_used; ++b) tma_load_2d(smem_w + (size_t)(b - g.tblk) * WA_BLK, &mapW, &wfull[0], 0, b * 128);
                 }
             } else {
                 uint32_t st = 0, ph = 0;
@@ -281,14 +345,17 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
         } else if (warp == 1) {
             // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
-            const uint32_t idesc = umma_idesc_bf16(128, g.N);
+            const int positions = g.H * g.pitch;
             uint32_t xst = 0, xph = 0, wst = 0, wph = 0, as = 0, aph = 0;
-            if (g.resident && (int)blockIdx.x < total_tiles) mbar_wait(&wfull[0], 0);
+            if (g.resident && nblk_used > g.tblk && (int)blockIdx.x < total_tiles) mbar_wait(&wfull[0], 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = g.n_tiles > 1 ? tile / g.n_tiles : tile;
                 const int ti = mt - (int)__umulhi((uint32_t)mt, g.inv_tpi) * g.tiles_per_img;
                 const int q0 = ti * g.adv;
                 const int idx0 = q0 - ((int)__umulhi((uint32_t)q0, g.inv_pitch) - 1) * g.pitch;   // row (128 B) of position q0 inside the box buffer
+                // the last tile of an image covers what is left of it: a narrower instruction (N in steps of 16; PAIR needs
+                // one more column for the second tap of its last position)
+                const uint32_t idesc = umma_idesc_bf16(128, min(g.N, (min(g.adv, positions - q0) + (PAIR ? 1 : 0) + 15) & ~15));
                 mbar_wait(&tempty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * g.tstride;
@@ -299,13 +366,32 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tc_fence_after();
                     const uint32_t xbase = smem_u32(smem_x + (size_t)xst * g.stage_bytes) + (uint32_t)(idx0 * 128);
                     const int nslots = seg0 ? g.slots0 : 1;
-                    for (int sl = 0; sl < nslots; ++sl, ++blk) {
-                        int shift = 0;
-                        if (seg0) {
-                            if (PAIR) shift = sl < 3 ? (sl - 1) * g.pitch - 1 : (sl - 4) * g.pitch + 1;
-                            else shift = (sl / 3 - 1) * g.pitch + (sl % 3 - 1);
+                    auto shift_of = [&](int sl) {
+                        if (!seg0) return 0;
+                        if (PAIR) return sl < 3 ? (sl - 1) * g.pitch - 1 : (sl - 4) * g.pitch + 1;
+                        return (sl / 3 - 1) * g.pitch + (sl % 3 - 1);
+                    };
+                    int sl = 0;
+                    // blocks held in tensor memory (the first g.tblk of chunk 0): TS-mode MMAs.  A loop of its own -- a predicated-off
+                    // tcgen05.mma inside a shared loop body costs ~40 cycles per instruction (tools/micro/ts_mma_test.cu)
+                    const int nts = ch == 0 ? min(g.tblk, nslots) : 0;
+                    for (; sl < nts; ++sl, ++blk) {
+                        if (elect_one()) {
+                            const uint32_t a_tm = tmem_base + (uint32_t)(g.tcol0 + 32 * blk);
+                            const uint64_t bdesc = umma_desc_sw128(xbase + (uint32_t)(shift_of(sl) * 128));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (!(g.dbg & 2)) umma_bf16_ts(d_tmem, a_tm + 8 * j, bdesc + 2 * j, idesc, (sl | j) != 0);
+                            if (sl == nslots - 1) {
+                                umma_commit(&xempty[xst]);
+                                if (ch == nchunks - 1) umma_commit(&tfull[as]);
+                            }
                         }
-                        uint32_t wslot = (uint32_t)blk;
+                        __syncwarp();
+                    }
+                    for (; sl < nslots; ++sl, ++blk) {
+                        const int shift = shift_of(sl);
+                        uint32_t wslot = (uint32_t)(blk - g.tblk);
                         if (!g.resident) {
                             mbar_wait(&wfull[wst], wph);
                             tc_fence_after();
@@ -424,7 +510,6 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         constexpr int CV = PAIR ? 2 : 4;                     // channel sub-blocks of 8 per thread
         constexpr int EQ = wa_ewarps(FUSE) / 4;              // warps per quarter
         const uint32_t stage = smem_u32(smem_o + (warp - 4) * 16 * SP);
-        const int nhu = g.N >> 4;
         const int HW = g.H * g.W;
         uint32_t as = 0, aph = 0;
         // per-thread channels: cbase + 8*v + t8, v = 0..CV-1 (fragment rows t8 / t8+8 of the two 16-lane halves).  The per-channel
@@ -447,6 +532,7 @@ conv_wa_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (g.n_tiles > 1) { mt = tile / g.n_tiles; nt = tile - mt * g.n_tiles; }
             const int n = (int)__umulhi((uint32_t)mt, g.inv_tpi), ti = mt - n * g.tiles_per_img;
             const int q0 = ti * g.adv;
+            const int nhu = (min(g.adv, HW + g.H - q0) + 15) >> 4;   // half-units with positions of the image (fewer in its last tile)
             const int cbase = nt * g.ctile + q * (PAIR ? 16 : 32);   // first channel of this warp
             bf16* const obase = p.out + (size_t)n * HW * p.Cout + cbase;
             float addv[CV];

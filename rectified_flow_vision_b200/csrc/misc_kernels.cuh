@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
                                                    float* __restrict__ out, int mc, int td, float* __restrict__ save_emb,
                                                    float* __restrict__ save_z1, float* __restrict__ save_h1,
                                                    float* __restrict__ save_z2) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     // save_*: training only -- the sinusoidal embedding and the two pre-activations, read by the time-MLP backward
     extern __shared__ float sm[];
     float* emb = sm;        // [mc]
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ t, 
 __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict__ act, const float* __restrict__ wcat,
                                                         const float* __restrict__ bcat, float* __restrict__ proj,
                                                         int rows, int td, int sumC) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     extern __shared__ float sm[];  // [8][td]
     const int r0 = blockIdx.y * 8;
     const int nr = min(8, rows - r0);
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict_
 
 // t_i = i * dt in double, rounded once to fp32: what `torch.full((B,), i * dt)` holds in models/base_flow.py:163-166
 __global__ void fill_step_times_kernel(float* __restrict__ t, int n, double dt) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) t[i] = (float)((double)i * dt);
 }
@@ -108,6 +114,8 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
                                                          const float* __restrict__ tvec, const float* __restrict__ wt,
                                                          const float* __restrict__ bias, bf16* __restrict__ out,
                                                          float* __restrict__ stats, int H, int W, int Cout, int slab_shift) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     // One thread = TWO horizontally adjacent output pixels x all C_out channels (16 at a time): the 3x4 input patch per
     // channel lives in registers and every broadcast weight vector read from shared memory feeds 8 FMAs instead of 4 (the
     // one-pixel version was bound by the shared-memory pipe: ncu l1tex 89 %, short-scoreboard stalls).
@@ -226,6 +234,8 @@ __global__ void __launch_bounds__(256, 2) input_conv_mma_kernel(const float* __r
                                                                 const float* __restrict__ tvec, const float* __restrict__ wt,
                                                                 const float* __restrict__ bias, bf16* __restrict__ out,
                                                                 float* __restrict__ stats, int H, int W, int Cout, int slab_shift) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     constexpr int K = CIN * 9, KS = (K + 15) / 16;
     extern __shared__ float ism[];
     float* xs = ism;                                     // [CIN][IM_TH + 2][IM_XP]
@@ -394,6 +404,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        bf16* __restrict__ out, int Ca, int Cb, int HW, int slab_shift,
                                                        int apply_silu, int pix_per_block, float eps, uint32_t drop_thresh,
                                                        uint32_t drop_seed, float drop_scale) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     // drop_thresh != 0 (training only): nn.Dropout after the SiLU (models/unet.py:62), mask from train_kernels.cuh
     // blockDim.x is a multiple of C/8, so every thread owns ONE 8-channel vector position for the whole block and
     // keeps its scale/shift in registers; the streaming loop is then load -> 8 FMAs (+SiLU) -> store.
@@ -504,6 +516,8 @@ __global__ void __launch_bounds__(256) output_conv_kernel(const bf16* __restrict
                                                           float* __restrict__ traj, const float* __restrict__ x0,
                                                           const float* __restrict__ x1, float* __restrict__ mse_acc,
                                                           int C, int H, int W, int Cout, int B, int mode, float dt) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     extern __shared__ __align__(16) uint8_t smraw[];
     const int pitch = C * 2 + 16;                                  // bytes per staged pixel / weight row
     const int tile_bytes = (OC_TH + 2) * (OC_TW + 2) * pitch;
@@ -619,6 +633,8 @@ __global__ void __launch_bounds__(256, 2) output_conv_z_kernel(const bf16* __res
                                                                float* __restrict__ traj, const float* __restrict__ x0,
                                                                const float* __restrict__ x1, float* __restrict__ mse_acc,
                                                                int H, int W, int Cout, int B, int mode, float dt) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): no-ops unless launched with the attribute
+    pdl_launch();
     constexpr int C = KS * 16;
     constexpr int pitch = C * 2 + 16;
     extern __shared__ __align__(16) uint8_t smraw[];

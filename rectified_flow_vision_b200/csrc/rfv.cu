@@ -60,6 +60,19 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+// One launch of a forward-path kernel; pdl = with the programmatic-stream-serialization attribute (common.cuh: pdl_wait).
+template <typename... KA, typename... A>
+static cudaError_t klaunch(bool pdl, void (*k)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, k, std::forward<A>(args)...);
+}
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -111,6 +124,7 @@ struct RunCtx {
     // rows 0 .. num_steps-1 of the projection table; step i then reads row temb_row and skips the time-MLP kernels.  -1: off.
     int temb_row = -1;
     bool temb_only = false;   // run just the time-MLP ops (the table fill)
+    bool pdl = false;         // launch with programmatic dependent launch (set by run_forward: sampling engines, not while profiling)
 };
 
 struct Op {
@@ -222,6 +236,7 @@ struct rfv_engine {
     struct LoopGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
     std::map<std::tuple<int, int, int>, LoopGraph> loop_graphs;
     bool use_graphs = true;    // RFV_FLAG_NO_GRAPH clears it
+    bool use_pdl = true;       // RFV_FLAG_NO_PDL clears it: kernels of a sampling chain launched as programmatic dependents
     cudaEvent_t ev_fork = nullptr, ev_join[2]{};
     // Gradient buckets for a data-parallel caller: slots are laid out in the order their gradients become final during the
     // backward pass, and cut into a few contiguous ranges; run_backward records, per bucket, an event on each backward stream
@@ -488,6 +503,42 @@ struct rfv_engine {
             g.a_stages = std::min(4, (avail - wregion) / g.stage_bytes);
         }
         if (g.a_stages < 2) return fail(RFV_ERR_INVALID, "conv %s: weights-as-A tile does not fit shared memory", L->name.c_str());
+        g.tblk = 0; g.tcol0 = 0; g.wa = nullptr;
+        // Weight blocks in TENSOR MEMORY.  Two accumulator stages of N = 192 columns leave 128 of the 512 columns free: four
+        // 128 x 64 weight blocks (32 columns each) move there and are multiplied in TS mode (A operand from TMEM, same rate as
+        // the shared-memory form at this N).  That returns 64 KB of shared memory to the box ring, which is what the layers with
+        // shortcut / residual chunks lack: with one full-size stage per chunk type the reload of a tile's main box cannot start
+        // before its own MMAs have finished (measured: 5,000 cycles per tile against 2,700 of MMAs on the 64->64 + identity
+        // layers), and the layers whose blocks do not fit next to two stages otherwise stream 144 KB of weights per tile or fall
+        // back to N = 128 tiles.  RFV_WA_TMEM: 0 = off, 1 = where it replaces streamed weights, N <= 160 tiles or a two-stage ring
+        // under multi-chunk tiles, 2 (default) = every layer it fits with three box stages (also the single-chunk 64->64 convs).
+        // Same-box measurements (tools/ab_tmem.sh, tools/pairs_ab.py): 64->64 + identity 0.266 -> 0.233 ms, 64->64 + 128-channel
+        // shortcut 0.265 -> 0.225, 64->128 0.133 -> 0.102 per 512 images; the single-chunk 64->64 convs are 4 % SLOWER timed alone
+        // (0.191 -> 0.199: 22 tiles of 192 instead of 17 of 256) but the power-capped production loop is not: 584 / 588 / 590
+        // pairs/s for modes 0 / 1 / 2 (TS-mode MMAs read a third less shared memory per instruction).
+        static const int tmode = getenv("RFV_WA_TMEM") ? atoi(getenv("RFV_WA_TMEM")) : 2;
+        if (tmode > 0 && g.n_tiles == 1 && !getenv("RFV_WA_N")) {
+            const WaGeom keep = g;
+            const int T = std::min(4, g.slots0);
+            const int chunks = g.cch0 + g.cch1a + g.cch1b + (may_resid ? g.ctile / 64 : 0);
+            shape(192);
+            const long wbytes = (long)(nblk_max - T) * WA_BLK;
+            const int st = wbytes >= 0 ? (int)std::min<long>(4, (avail - wbytes) / g.stage_bytes) : 0;
+            bool take = false;
+            // three stages or nothing: with two, a 64->64 conv with a 192-channel shortcut (four chunks per tile) measured 0.358 ms
+            // against 0.344 ms on streamed weights at N = 256
+            if (st >= 3) take = !keep.resident || keep.N <= 160 || (chunks >= 2 && keep.a_stages < 3) || tmode >= 2;
+            if (take) {
+                g.inv_tpi = (uint32_t)((0x100000000ull + g.tiles_per_img - 1) / g.tiles_per_img);
+                g.tstages = 2; g.tstride = 192;
+                g.tblk = T; g.tcol0 = 384;
+                g.resident = 1; g.w_stages = 1; g.a_stages = st;
+                if (g.rows % g.rs != 0) g.rs = 1;
+                wregion = (int)wbytes;
+            } else {
+                g = keep;
+            }
+        }
         *smem = 2048 + (size_t)g.a_stages * g.stage_bytes + wregion + wa_staging_bytes(pair, fuse) + 512;
         return 0;
     }
@@ -539,13 +590,14 @@ struct rfv_engine {
                            (out->W == 32 || out->W == 64 || out->W == 128) && (!resid || resid->C == L->Cout);
         if (wa_ok) {
             // weights-as-A kernel (conv_wa.cuh): N = up to 256 positions per MMA, optional in-kernel GroupNorm on segment 0
-            struct WBundle { CUtensorMap a0, a0b, a1, a2, r, w; WaGeom g; size_t smem; bool pair, fuse; };
+            struct WBundle { CUtensorMap a0, a0b, a1, a2, r, w; WaGeom g; size_t smem; bool pair, fuse; const void* wa; };
             auto bd = std::make_shared<WBundle>();
             WaGeom& g = bd->g;
             bd->pair = L->Cout % 128 != 0;
             bd->fuse = fr != nullptr;
             RFV_TRY(plan_wa(&g, &bd->smem, L, out->W, out->H, resid != nullptr || acc_of != nullptr, in0->C / 64, fr != nullptr));
             RFV_TRY(ensure_wa(L, g));
+            bd->wa = L->wa;
             auto amap = [&](CUtensorMap* m, const ActP& t) {
                 return make_map4(m, t->p, t->C, t->W, t->H, cap, t->C, (size_t)t->W * t->C, (size_t)t->H * t->W * t->C, g.pitch, g.rs, 1);
             };
@@ -568,15 +620,11 @@ struct rfv_engine {
                 g.cchr = q.resid ? g.ctile / 64 : 0;
                 if (g.cchr && !getenv("RFV_WA_PF")) g.pf = 1;   // two boxes per tile through a short ring: prefetch the next tile's into L2
                 g.m_tiles = rc.B * g.tiles_per_img;
+                g.wa = bd->wa;
                 const int grid = std::min(g.m_tiles * g.n_tiles, sms);
-                if (bd->fuse) {
-                    if (bd->pair) conv_wa_kernel<true, true><<<grid, wa_threads(true), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                    else conv_wa_kernel<false, true><<<grid, wa_threads(true), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                } else {
-                    if (bd->pair) conv_wa_kernel<true, false><<<grid, wa_threads(false), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                    else conv_wa_kernel<false, false><<<grid, wa_threads(false), bd->smem, s>>>(bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
-                }
-                return cudaGetLastError();
+                auto kern = bd->fuse ? (bd->pair ? conv_wa_kernel<true, true> : conv_wa_kernel<false, true>)
+                                     : (bd->pair ? conv_wa_kernel<true, false> : conv_wa_kernel<false, false>);
+                return klaunch(rc.pdl, kern, dim3(grid), dim3(wa_threads(bd->fuse)), bd->smem, s, bd->a0, bd->a0b, bd->a1, bd->a2, bd->r, bd->w, q, g);
             });
         } else if (fr) {
             return fail(RFV_ERR_STATE, "internal: conv %s cannot fuse its GroupNorm", L->name.c_str());
@@ -668,11 +716,13 @@ struct rfv_engine {
                     lp.gridDim = dim3(std::min(pairs, bd->pair_clusters) * 2);
                     lp.blockDim = dim3(UMMA_THREADS);
                     lp.stream = s;
-                    cudaLaunchAttribute ap[1];
+                    cudaLaunchAttribute ap[2];
                     ap[0].id = cudaLaunchAttributeClusterDimension;
                     ap[0].val.clusterDim.x = 2; ap[0].val.clusterDim.y = 1; ap[0].val.clusterDim.z = 1;
+                    ap[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    ap[1].val.programmaticStreamSerializationAllowed = 1;
                     lp.attrs = ap;
-                    lp.numAttrs = 1;
+                    lp.numAttrs = rc.pdl ? 2 : 1;
                     if (bd->BN == 256) {
                         lp.dynamicSmemBytes = PairCfg<256>::SMEM_BYTES;
                         return cudaLaunchKernelEx(&lp, conv_umma2_kernel<256>, bd->a0, bd->a1, bd->a2, bd->w, q, g);
@@ -685,11 +735,20 @@ struct rfv_engine {
                 lc.gridDim = dim3(std::min(super_tiles, bd->max_clusters) * g.cluster);
                 lc.blockDim = dim3(UMMA_THREADS);
                 lc.stream = s;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cudaLaunchAttribute at[2];
+                int na = 0;
+                if (g.cluster > 1) {
+                    at[na].id = cudaLaunchAttributeClusterDimension;
+                    at[na].val.clusterDim.x = g.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+                    ++na;
+                }
+                if (rc.pdl) {
+                    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[na].val.programmaticStreamSerializationAllowed = 1;
+                    ++na;
+                }
                 lc.attrs = at;
-                lc.numAttrs = g.cluster > 1 ? 1 : 0;
+                lc.numAttrs = na;
                 switch (bd->BN) {
                     case 256:
                         lc.dynamicSmemBytes = UmmaCfg<256>::SMEM_BYTES;
@@ -714,8 +773,7 @@ struct rfv_engine {
                 q.temb_stride = rc.t ? sumC_ : 0;
                 if (rc.temb_row > 0 && q.temb) q.temb += (size_t)rc.temb_row * sumC_;
                 dim3 grid((unsigned)(((size_t)rc.B * HoWo + MMA_BM - 1) / MMA_BM), cout / MMA_BN);
-                conv_mma_kernel<<<grid, 256, 0, s>>>(q);
-                return cudaGetLastError();
+                return klaunch(rc.pdl, conv_mma_kernel, grid, dim3(256), 0, s, q);
             });
         }
         return 0;
@@ -767,9 +825,8 @@ struct rfv_engine {
             while (ppb_run > 64 && ((HW + ppb_run - 1) / ppb_run) * rc.B < 8 * sms_) ppb_run /= 2;
             dim3 grid((HW + ppb_run - 1) / ppb_run, rc.B);
             const uint32_t dt_ = drop ? rc.drop_thresh : 0u;
-            gn_apply_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss, silu ? silu_mode : 0, ppb_run, 1e-5f,
-                                                                         dt_, rc.seed ^ ((uint32_t)site_id * 0x9E3779B9u), rc.drop_scale);
-            return cudaGetLastError();
+            return klaunch(rc.pdl, gn_apply_kernel, grid, dim3(threads), 2 * C * sizeof(float), s, xa, xb, sa, sb, gam, bet, o, Ca, Cb, HW, ss,
+                           silu ? silu_mode : 0, ppb_run, 1e-5f, dt_, rc.seed ^ ((uint32_t)site_id * 0x9E3779B9u), rc.drop_scale);
         });
         set_last_bytes(4.0 * C * HW);   // 2 B read + 2 B written per element
         return 0;
@@ -791,8 +848,7 @@ struct rfv_engine {
         const int Ca = srcs[0]->C, Cb = srcs.size() > 1 ? srcs[1]->C : 0, ss = slab_shift;
         const float *gam = pf(ig), *bet = pf(ib);
         push("gn_coef", "gn:" + name, 0.0, [=](const RunCtx& rc, cudaStream_t s) {
-            gn_coef_kernel<<<rc.B, 256, 0, s>>>(sa, sb, gam, bet, coef, Ca, Cb, HW, ss, 1e-5f);
-            return cudaGetLastError();
+            return klaunch(rc.pdl, gn_coef_kernel, dim3(rc.B), dim3(256), 0, s, sa, sb, gam, bet, coef, Ca, Cb, HW, ss, 1e-5f);
         });
         *coef_out = coef;
         return 0;
@@ -1204,15 +1260,13 @@ int rfv_engine::build() {
         push("temb", "temb:time_mlp", 2.0 * (mc * td + td * td), [=](const RunCtx& rc, cudaStream_t s) {
             const int rows = rc.t ? rc.B : 1;
             float *se = rc.train ? temb_emb : nullptr, *s1 = rc.train ? temb_z1 : nullptr, *s2 = rc.train ? temb_z2 : nullptr;
-            temb_kernel<<<dim3(rows, rows >= 64 ? 1 : 8), 256, (mc_ + td_) * sizeof(float), s>>>(rc.t, rc.t ? 0 : 1, rc.t_scalar, w1, b1, w2, b2, act, mc_, td_, se, s1,
-                                                                        rc.train ? temb_h1 : nullptr, s2);
-            return cudaGetLastError();
+            return klaunch(rc.pdl, temb_kernel, dim3(rows, rows >= 64 ? 1 : 8), dim3(256), (mc_ + td_) * sizeof(float), s, rc.t, rc.t ? 0 : 1, rc.t_scalar,
+                           w1, b1, w2, b2, act, mc_, td_, se, s1, rc.train ? temb_h1 : nullptr, s2);
         });
         push("temb", "temb:block_projections", 2.0 * td * sumC, [=](const RunCtx& rc, cudaStream_t s) {
             const int rows = rc.t ? rc.B : 1;
             dim3 grid((sumC_ + 63) / 64, (rows + 7) / 8);
-            temb_proj_kernel<<<grid, 256, 8 * td_ * sizeof(float), s>>>(act, wc, bc, proj, rows, td_, sumC_);
-            return cudaGetLastError();
+            return klaunch(rc.pdl, temb_proj_kernel, grid, dim3(256), 8 * td_ * sizeof(float), s, act, wc, bc, proj, rows, td_, sumC_);
         });
         if (train) {
             // backward of the time MLP: runs last (first block recorded), after every ResidualBlock has added its
@@ -1273,7 +1327,7 @@ int rfv_engine::build() {
             if (im) {
                 const int tiles_img = ((S + IM_TW - 1) / IM_TW) * ((S + IM_TH - 1) / IM_TH);
                 dim3 grid((tiles_img + IM_TPB - 1) / IM_TPB, rc.B);
-#define RFV_IM_LAUNCH(CI, NT) input_conv_mma_kernel<CI, NT><<<grid, 256, im_smem, s>>>(rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss)
+#define RFV_IM_LAUNCH(CI, NT) return klaunch(rc.pdl, input_conv_mma_kernel<CI, NT>, grid, dim3(256), im_smem, s, rc.x, rc.x1, rc.t, wt, b, o, st, S, S, mc, ss)
                 if (im_ntc == 8) {
                     switch (Cin) {
                         case 1: RFV_IM_LAUNCH(1, 8); break;
@@ -1408,17 +1462,14 @@ int rfv_engine::build() {
             push("attention", "attn:mid_attn", 4.0 * C * (double)N * N, [=](const RunCtx& rc, cudaStream_t s) {
                 float* l = rc.train ? lse : nullptr;
                 if (au) {
-                    attn_umma_kernel<<<dim3(N / 128, heads, rc.B), AU_THREADS, AU_SMEM, s>>>(*amap, op, N, C, sl2, l);
-                    return cudaGetLastError();
+                    return klaunch(rc.pdl, attn_umma_kernel, dim3(N / 128, heads, rc.B), dim3(AU_THREADS), AU_SMEM, s, *amap, op, N, C, sl2, l);
                 }
                 if (ak) {
-                    attn_umma_kv_kernel<<<dim3(N / 128, heads, rc.B), AK_THREADS, AK_SMEM, s>>>(*amap, op, N, C, sl2, l);
-                    return cudaGetLastError();
+                    return klaunch(rc.pdl, attn_umma_kv_kernel, dim3(N / 128, heads, rc.B), dim3(AK_THREADS), AK_SMEM, s, *amap, op, N, C, sl2, l);
                 }
                 dim3 grid(N / 64, heads, rc.B);
-                if (d == 64) attn_kernel<64><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
-                else attn_kernel<32><<<grid, 128, 0, s>>>(qp, op, N, C, sl2, l);
-                return cudaGetLastError();
+                if (d == 64) return klaunch(rc.pdl, attn_kernel<64>, grid, dim3(128), 0, s, qp, op, N, C, sl2, l);
+                return klaunch(rc.pdl, attn_kernel<32>, grid, dim3(128), 0, s, qp, op, N, C, sl2, l);
             });
         }
         release(qkv);
@@ -1561,13 +1612,11 @@ int rfv_engine::build() {
             const int ntiles = ((S + OC_TW - 1) / OC_TW) * ((S + OC_TH - 1) / OC_TH) * rc.B;
             const int grid = std::min(ntiles, 2 * sms);
             if (oz) {
-                if (C == 32) output_conv_z_kernel<2><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
-                else if (C == 64) output_conv_z_kernel<4><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
-                else output_conv_z_kernel<8><<<grid, 256, zsmem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
-                return cudaGetLastError();
+                auto kz = C == 32 ? output_conv_z_kernel<2> : (C == 64 ? output_conv_z_kernel<4> : output_conv_z_kernel<8>);
+                return klaunch(rc.pdl, kz, dim3(grid), dim3(256), zsmem, s, ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, S, S, Co, rc.B, rc.mode, rc.dt);
             }
-            output_conv_kernel<<<grid, 256, smem, s>>>(ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.B, rc.mode, rc.dt);
-            return cudaGetLastError();
+            return klaunch(rc.pdl, output_conv_kernel, dim3(grid), dim3(256), smem, s, ap, wpk, b, rc.out, rc.traj, rc.tgt_x0, rc.tgt_x1, rc.mse, C, S, S, Co, rc.B,
+                           rc.mode, rc.dt);
         });
         if (train) {
             // backward of the output conv: dv (fp32 NCHW, written by the forward in mode 3) -> weight / bias gradient,
@@ -1663,7 +1712,15 @@ int rfv_engine::build() {
     return 0;
 }
 
-int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
+int rfv_engine::run_forward(const RunCtx& rc_in, cudaStream_t s) {
+    RunCtx rc = rc_in;
+    // programmatic dependent launch for every kernel but the first of the pass (its predecessor is the memset node below)
+    // Small micro-batches only: measured on one box, batch 64: 1.402 vs 1.428 ms per velocity evaluation (kernels of 10-30 us, the
+    // launch gap and the prologue are a visible share); micro-batch 512: 8.45 vs 8.35 ms -- the dependents' CTAs hold the SMs they
+    // land on while they wait, which costs more there than the prologues they hide.  RFV_PDL_MAX overrides the bound.
+    static const int pdl_max = getenv("RFV_PDL_MAX") ? atoi(getenv("RFV_PDL_MAX")) : 128;
+    const bool pdl_ok = use_pdl && !profiling && !rc.train && rc.B <= pdl_max;
+    rc.pdl = false;
     for (auto& p : params)
         if (!p.loaded) return fail(RFV_ERR_STATE, "parameter %s was never uploaded (rfv_set_tensor)", p.name.c_str());
     if (rc.B < 1 || rc.B > cap) return fail(RFV_ERR_STATE, "micro-batch %d outside [1,%d]", rc.B, cap);
@@ -1691,6 +1748,7 @@ int rfv_engine::run_forward(const RunCtx& rc, cudaStream_t s) {
         cudaError_t e = op.run(rc, s);
         if (e != cudaSuccess) return fail(RFV_ERR_CUDA, "launch of %s failed: %s", op.label.c_str(), cudaGetErrorString(e));
         ++launches;
+        rc.pdl = pdl_ok;
         if (profiling) CU_CHECK(cudaEventRecord(prof_events[i].second, s));
     }
     if (profiling) {
@@ -1862,6 +1920,7 @@ RFV_EXPORT int rfv_create(const rfv_config* cfg, rfv_handle* out) {
     e->use_wa = !(cfg->flags & RFV_FLAG_NO_WA);
     e->use_lanes = !(cfg->flags & RFV_FLAG_ONE_LANE) && !(cfg->flags & RFV_FLAG_TRAIN);
     e->use_graphs = !(cfg->flags & RFV_FLAG_NO_GRAPH);
+    e->use_pdl = !(cfg->flags & RFV_FLAG_NO_PDL) && !(cfg->flags & RFV_FLAG_TRAIN);
     e->two_streams = !(cfg->flags & RFV_FLAG_ONE_STREAM);
     e->fuse_mode = (cfg->flags & RFV_FLAG_FUSE_GN) ? 2 : ((cfg->flags & RFV_FLAG_NO_FUSE_GN) ? 0 : 1);
     e->train = (cfg->flags & RFV_FLAG_TRAIN) != 0;

@@ -188,7 +188,7 @@ NO_WA = 1048576   # RFV_FLAG_NO_WA: per-tap implicit-GEMM kernel instead of the 
                                        (8192, "mma.sync attention"), (32768, "exp-form SiLU"), (65536, "tap-shifted output conv"),
                                        (131072, "fp32-FMA input conv"), (262144, "time MLP per Euler step"), (524288, "no GroupNorm fusion"),
                                        (1, "mma.sync implicit-GEMM convs (no tcgen05)"), (8388608, "single-CTA 256-channel convs (no CTA pairs)"),
-                                       (4194304, "no loop graphs")])
+                                       (4194304, "no loop graphs"), (16777216, "no programmatic dependent launch")])
 def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
     """The A/B kernels kept behind RFV_FLAG_* (include/rfv.h) compute the same velocity as the default plan."""
     from rectified_flow_vision_b200 import engine as E
@@ -203,3 +203,30 @@ def test_opt_in_kernel_variants_agree_with_the_default(flag, name):
     assert np.isfinite(outs[1]).all(), name
     assert util.rel_l2(outs[1], outs[0]) <= 2e-2, (name, util.rel_l2(outs[1], outs[0]))
     assert util.rel_l2(outs[1], g["v"]) <= 3e-2, name
+
+
+NO_PDL = 16777216   # RFV_FLAG_NO_PDL: every kernel fully serialised behind its predecessor
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,mb,steps", [(6, 8, 8), (40, 16, 4), (1, 4, 12)])
+def test_programmatic_dependent_launch_matches_serial_launch(rows, mb, steps):
+    """Sampling chains launch every kernel but the first of a pass as a programmatic dependent of its predecessor (the next
+    kernel's prologue runs under the previous one's tail and stops in griddepcontrol.wait).  A missing wait would be a race
+    between neighbouring kernels: the multi-step result (loop graph, one and two lanes, short kernels at small batches) must
+    equal the fully serialised chain's up to the summation-order noise of the GroupNorm statistics, run after run."""
+    from rectified_flow_vision_b200 import engine as E
+    m = _model("default64")
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(rows, 3, 64, 64, generator=gen).cuda()
+    res = {}
+    for fl in (NO_PDL, 0):
+        eng = E.Engine(m.velocity_net.arch(), 64, torch.device("cuda:0"), micro_batch=mb, flags=fl)
+        eng.sync_weights(m.velocity_net)
+        res[fl] = [eng.euler_sample(x, steps)[0].cpu().numpy() for _ in range(3)]
+    ref = res[NO_PDL][0]
+    assert np.isfinite(ref).all()
+    noise = max(util.rel_l2(r, ref) for r in res[NO_PDL][1:])   # run-to-run spread of the serial chain itself
+    for r in res[0]:
+        assert np.isfinite(r).all()
+        assert util.rel_l2(r, ref) <= max(5e-3, 4 * noise), (util.rel_l2(r, ref), noise)
