@@ -195,6 +195,25 @@ int rfv_bind_param(rfv_handle h, const char* name, float* dev_ptr);
  * bf16 copies.  grad_norm_out (optional, DEVICE): the pre-clip global gradient norm. */
 int rfv_optimizer_step(rfv_handle h, const rfv_adamw* hyper, float* grad_norm_out, void* stream);
 
+/* ---- quality metrics on device tensors ------------------------------------------------------------------------
+ * Stateless (no handle); all pointers are DEVICE pointers.  They replace the numpy / scipy / skimage arithmetic of
+ * MetricsCalculator (utils/metrics.py:39-116) for tensors that already live in HBM (the sampler's output). */
+/* mu[j] = mean over the n rows of x [n][d] (fp32); mu: [d] fp64.  np.mean(images_flat, axis=0), utils/metrics.py:85. */
+int rfv_metrics_mean(const float* x, int64_t n, int64_t d, double* mu, void* stream);
+/* sigma = (x - mu)^T (x - mu) / (n - 1), [d][d] fp64: np.cov(images_flat, rowvar=False), utils/metrics.py:86.  n >= 2. */
+int rfv_metrics_covariance(const float* x, const double* mu, int64_t n, int64_t d, double* sigma, void* stream);
+/* The pieces of MetricsCalculator.compute_fid (utils/metrics.py:89-116) without forming a d x d matrix:
+ *   terms[0] = |mu1 - mu2|^2, terms[1] = tr sigma1, terms[2] = tr sigma2,
+ *   gram [n1][n2] fp64 = (x1 - mu1)(x2 - mu2)^T / sqrt((n1-1)(n2-1)): its singular values sum to tr sqrtm(sigma1 sigma2),
+ * so FID = terms[0] + terms[1] + terms[2] - 2 * sum(svdvals(gram)).  n1, n2 >= 2. */
+int rfv_metrics_fid_terms(const float* x1, const double* mu1, int64_t n1, const float* x2, const double* mu2, int64_t n2, int64_t d,
+                          double* gram, double* terms, void* stream);
+/* Mean structural similarity of `batch` image pairs a, b [batch][channels][height][width] fp32 -> out [batch] fp64:
+ * skimage.metrics.structural_similarity(channel_axis, data_range) with its defaults (7x7 uniform window, K1 = 0.01, K2 = 0.03,
+ * sample covariance, mean over the image cropped by 3 pixels), as called at utils/metrics.py:52.  height, width >= 7. */
+int rfv_metrics_ssim(const float* a, const float* b, int64_t batch, int channels, int height, int width, float data_range,
+                     double* out, void* stream);
+
 /* ---- introspection for tests / bench -------------------------------------------------------------------- */
 /* Number of engine kernels launched (or graph-replayed) since the last call with reset != 0. */
 int64_t rfv_launch_count(rfv_handle h, int reset);

@@ -27,6 +27,7 @@
 #include "conv_wa.cuh"
 #include "conv_umma.cuh"
 #include "conv_umma2.cuh"
+#include "metrics.cuh"
 #include "misc_kernels.cuh"
 #include "rfv.h"
 #include "train_kernels.cuh"
@@ -2548,6 +2549,64 @@ RFV_EXPORT int64_t rfv_debug_activation(rfv_handle h, const char* name, float* d
     nhwc_to_nchw_kernel<<<512, 256, 0, (cudaStream_t)stream>>>(a.p, dev_out, B, a.C, a.H * a.W);
     if (cudaGetLastError() != cudaSuccess) return fail(RFV_ERR_CUDA, "debug copy launch failed");
     return (int64_t)B * per_img;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// quality metrics on device tensors (metrics.cuh; utils/metrics.py:39-116 of the reference) -- stateless entry points
+// ---------------------------------------------------------------------------------------------------------
+RFV_EXPORT int rfv_metrics_mean(const float* x, int64_t n, int64_t d, double* mu, void* stream) {
+    if (!x || !mu || n < 1 || d < 1 || n > (1 << 30) || d > (1 << 30)) return fail(RFV_ERR_INVALID, "rfv_metrics_mean: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(mu, 0, (size_t)d * sizeof(double), s));
+    const int slices = (int)std::min<int64_t>(64, (n + 31) / 32);
+    metrics_colsum_kernel<<<dim3((unsigned)((d + 255) / 256), slices), 256, 0, s>>>(x, (int)n, (int)d, mu);
+    metrics_scale_kernel<<<(unsigned)((d + 255) / 256), 256, 0, s>>>(mu, (int)d, 1.0 / (double)n);
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+RFV_EXPORT int rfv_metrics_covariance(const float* x, const double* mu, int64_t n, int64_t d, double* sigma, void* stream) {
+    if (!x || !mu || !sigma || d < 1 || d > (1 << 20)) return fail(RFV_ERR_INVALID, "rfv_metrics_covariance: bad argument");
+    if (n < 2 || n > (1 << 30)) return fail(RFV_ERR_INVALID, "rfv_metrics_covariance: needs at least two samples (got %lld)", (long long)n);
+    const unsigned t = (unsigned)((d + MG_T - 1) / MG_T);
+    metrics_gram_kernel<true><<<dim3(t, t), 256, 0, (cudaStream_t)stream>>>(x, x, mu, mu, (int)d, (int)d, (int)n, (int)d, 1.0 / (double)(n - 1), sigma);
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+RFV_EXPORT int rfv_metrics_fid_terms(const float* x1, const double* mu1, int64_t n1, const float* x2, const double* mu2, int64_t n2, int64_t d,
+                                     double* gram, double* terms, void* stream) {
+    if (!x1 || !mu1 || !x2 || !mu2 || !gram || !terms || d < 1 || d > (1 << 30)) return fail(RFV_ERR_INVALID, "rfv_metrics_fid_terms: bad argument");
+    if (n1 < 2 || n2 < 2 || n1 > (1 << 20) || n2 > (1 << 20))
+        return fail(RFV_ERR_INVALID, "rfv_metrics_fid_terms: needs at least two samples per set (got %lld, %lld)", (long long)n1, (long long)n2);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(terms, 0, 3 * sizeof(double), s));
+    metrics_sqdiff_kernel<<<64, 256, 0, s>>>(mu1, mu2, (int)d, terms);
+    metrics_sqdev_kernel<<<1024, 256, 0, s>>>(x1, mu1, (int)n1, (int)d, 1.0 / (double)(n1 - 1), terms + 1);
+    metrics_sqdev_kernel<<<1024, 256, 0, s>>>(x2, mu2, (int)n2, (int)d, 1.0 / (double)(n2 - 1), terms + 2);
+    const double scale = 1.0 / std::sqrt((double)(n1 - 1) * (double)(n2 - 1));
+    metrics_gram_kernel<false><<<dim3((unsigned)((n2 + MG_T - 1) / MG_T), (unsigned)((n1 + MG_T - 1) / MG_T)), 256, 0, s>>>(
+        x1, x2, mu1, mu2, (int)n1, (int)n2, (int)d, (int)d, scale, gram);
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+RFV_EXPORT int rfv_metrics_ssim(const float* a, const float* b, int64_t batch, int channels, int height, int width, float data_range,
+                                double* out, void* stream) {
+    if (!a || !b || !out || batch < 1 || batch > 65535 || channels < 1 || channels > 65535)
+        return fail(RFV_ERR_INVALID, "rfv_metrics_ssim: bad argument");
+    if (height < SS_WIN || width < SS_WIN)
+        return fail(RFV_ERR_INVALID, "rfv_metrics_ssim: the 7x7 window exceeds the image extent (%d x %d)", height, width);
+    const size_t smem = (size_t)2 * (SS_ROWS + 2 * SS_PAD) * width * sizeof(float);
+    if (smem > 48 * 1024) return fail(RFV_ERR_INVALID, "rfv_metrics_ssim: width %d unsupported (max %d)", width, (int)(48 * 1024 / (8 * (SS_ROWS + 2 * SS_PAD))));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(out, 0, (size_t)batch * sizeof(double), s));
+    const int hout = height - 2 * SS_PAD, wout = width - 2 * SS_PAD;
+    const double c1 = (0.01 * (double)data_range) * (0.01 * (double)data_range), c2 = (0.03 * (double)data_range) * (0.03 * (double)data_range);
+    metrics_ssim_kernel<<<dim3((unsigned)((hout + SS_ROWS - 1) / SS_ROWS), (unsigned)channels, (unsigned)batch), 256, smem, s>>>(
+        a, b, channels, height, width, c1, c2, 1.0 / ((double)hout * wout * channels), out);
+    CU_CHECK(cudaGetLastError());
+    return 0;
 }
 
 RFV_EXPORT int rfv_set_profiling(rfv_handle h, int enabled) {

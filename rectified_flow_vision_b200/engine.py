@@ -74,6 +74,10 @@ SYMBOLS = {
     "rfv_get_grad": (C.c_int, [_VP, C.c_char_p, _FP, _I64, C.c_float, _VP]),
     "rfv_bind_param": (C.c_int, [_VP, C.c_char_p, _FP]),
     "rfv_optimizer_step": (C.c_int, [_VP, C.POINTER(RfvAdamW), _FP, _VP]),
+    "rfv_metrics_mean": (C.c_int, [_FP, _I64, _I64, _VP, _VP]),
+    "rfv_metrics_covariance": (C.c_int, [_FP, _VP, _I64, _I64, _VP, _VP]),
+    "rfv_metrics_fid_terms": (C.c_int, [_FP, _VP, _I64, _FP, _VP, _I64, _I64, _VP, _VP, _VP]),
+    "rfv_metrics_ssim": (C.c_int, [_FP, _FP, _I64, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP]),
     "rfv_launch_count": (_I64, [_VP, C.c_int]),
     "rfv_flops_per_image": (C.c_double, [_VP]),
     "rfv_debug_activation": (_I64, [_VP, C.c_char_p, _FP, _I64, _VP]),

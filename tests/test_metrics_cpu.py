@@ -1,0 +1,50 @@
+"""CPU checks of the quality-metric oracle (oracle/metrics_oracle.py) against the reference's own tests
+(tests/test_utils.py:30-73 of the reference) and closed forms; no GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import metrics_oracle as M
+
+
+def test_ssim_reference_test_cases():
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 255, (64, 64, 3), dtype=np.uint8)
+    assert M.ssim(img, img) > 0.99                      # tests/test_utils.py:30-34
+    assert abs(M.ssim(img, img) - 1.0) < 1e-12
+    z, w = np.zeros((64, 64, 3), np.uint8), np.ones((64, 64, 3), np.uint8) * 255
+    assert M.ssim(z, w) < 0.5                           # tests/test_utils.py:36-41
+    c1 = (0.01 * 255) ** 2
+    assert abs(M.ssim(z, w) - c1 / (255.0 ** 2 + c1)) < 1e-15   # constant images: only the luminance term is left
+    with pytest.raises(ValueError):                     # tests/test_utils.py:43-49
+        M.ssim(img, img[:32, :32])
+
+
+def test_ssim_constant_images_closed_form_and_symmetry():
+    a, b = np.full((16, 20), 40.0), np.full((16, 20), 200.0)
+    c1 = (0.01 * 255) ** 2
+    assert abs(M.ssim(a, b) - (2 * 40 * 200 + c1) / (40 ** 2 + 200 ** 2 + c1)) < 1e-14
+    rng = np.random.default_rng(1)
+    x, y = rng.integers(0, 256, (24, 31, 3)).astype(np.uint8), rng.integers(0, 256, (24, 31, 3)).astype(np.uint8)
+    assert abs(M.ssim(x, y) - M.ssim(y, x)) < 1e-15
+    assert -1.0 <= M.ssim(x, y) <= 1.0
+
+
+def test_fid_reference_test_cases():
+    rng = np.random.default_rng(2)
+    images = rng.standard_normal((10, 3, 8, 8)).astype(np.float32)
+    mu, sigma = M.fid_statistics(images)                # tests/test_utils.py:51-58 (shape contract)
+    assert mu.shape == (192,) and sigma.shape == (192, 192) and sigma.dtype == np.float64
+    assert M.fid(images, images) < 1.0                  # tests/test_utils.py:60-65
+    other = (rng.standard_normal((10, 3, 8, 8)) * 2 + 1).astype(np.float32)
+    assert M.fid(images, other) > 0                     # tests/test_utils.py:67-73
+
+
+@pytest.mark.parametrize("n1,n2,shape", [(300, 280, (3, 6, 6)), (10, 12, (3, 8, 8)), (40, 7, (1, 9, 9))])
+def test_nuclear_norm_form_equals_the_sqrtm_form(n1, n2, shape):
+    """The identity the CUDA path rests on: tr sqrtm(sigma1 sigma2) = sum of the singular values of the cross Gram matrix."""
+    rng = np.random.default_rng(n1)
+    x1 = rng.standard_normal((n1,) + shape).astype(np.float32)
+    x2 = (rng.standard_normal((n2,) + shape) * 1.7 + 0.5).astype(np.float32)
+    ref, low = M.fid(x1, x2), M.fid_lowrank(x1, x2)
+    assert abs(ref - low) <= 1e-6 * abs(ref), (ref, low)
+    assert abs(M.fid_lowrank(x1, x1)) < 1e-9
