@@ -380,12 +380,15 @@ def run_ours(args):
     if world > 1:
         from rectified_flow_vision_b200 import dist as rdist
         job_noise = rdist.seeded_noise(world * P, CH, IMAGE, seed=4242).pin_memory()   # identical on every rank
-        rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True)   # warm (NCCL channels)
+        # the gathered result lands in ONE pinned host buffer the job re-uses (a fresh 805 MB pinned tensor per call costs ~0.3 s
+        # of page-locking at 8 ranks -- the caller of a repeated gather passes `out=`, as here)
+        g_out = torch.empty((world * P, CH, IMAGE, IMAGE), dtype=torch.float32, pin_memory=True)
+        rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True, out=g_out)   # warm (NCCL channels)
         barrier()
         t0 = time.perf_counter()
         g_steps = max(1, min(args.steps, 2))
         for _ in range(g_steps):
-            gx0, gx1 = rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True)
+            gx0, gx1 = rdist.generate_reflow_pairs_sharded(model, world * P, EULER_STEPS, noise=job_noise, gather=True, out=g_out)
         torch.cuda.synchronize()
         g_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
@@ -394,7 +397,7 @@ def run_ours(args):
                       "all_gather_bytes_per_rank_per_step": int(world * img_bytes),
                       "api": "dist.generate_reflow_pairs_sharded(model, num_pairs, 100, noise=<host tensor>, gather=True): shard -> "
                              "integrate -> ONE all_gather_into_tensor over NCCL -> full (x0, x1) on every rank's host"}
-        del gx0, gx1, job_noise
+        del gx0, gx1, job_noise, g_out
 
     # ---- BASELINE.json configs[4]: the config.yaml UNet at 128x128, seeded random-init weights, 8-step Euler, 128 images per
     #      GPU (batch 1,024 over 8 GPUs), inputs resident in HBM ----

@@ -28,16 +28,24 @@ def seeded_noise(num: int, channels: int, size: int, seed: int) -> torch.Tensor:
 
 
 def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, gather: bool = True,
-                group=None) -> torch.Tensor:
+                group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Apply `fn` to this rank's slice of `rows` (a CPU tensor identical on all ranks); optionally all-gather the
-    per-rank results back into row order.  `fn` maps a CPU tensor [k, ...] to a CPU tensor [k, ...]."""
+    per-rank results back into row order.  `fn` maps a CPU tensor [k, ...] to a tensor [k, ...] (CPU, or -- under NCCL -- on
+    this rank's GPU, which saves the device->host->device round trip of the shard).  `out` (optional, gather=True): a
+    contiguous CPU tensor [n, ...] that receives the gathered rows -- a caller that gathers repeatedly re-uses ONE (pinned)
+    buffer instead of page-locking a fresh one per call (805 MB at 8 GPUs x 2048 pairs: ~0.3 s per call, measured)."""
     if not (dist.is_available() and dist.is_initialized()):
-        return fn(rows)
+        res = fn(rows)
+        res = res.cpu() if res.device.type != "cpu" else res
+        if out is not None and gather:
+            out.copy_(res)
+            return out
+        return res
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(rows.shape[0], rank, world)
     local = fn(rows[lo:hi])
     if not gather:
-        return local
+        return local.cpu() if local.device.type != "cpu" else local
     backend = dist.get_backend(group)
     n = rows.shape[0]
     width = -(-n // world)  # equal-sized slots for the collective; short shards are padded
@@ -53,7 +61,9 @@ def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, 
         if hi - lo < width:
             slot[hi - lo:].zero_()
         dist.all_gather_into_tensor(gathered_dev, slot, group=group)
-        gathered = torch.empty(gathered_dev.shape, dtype=local.dtype, pin_memory=True)
+        direct = out is not None and width * world == n and tuple(out.shape) == tuple(gathered_dev.shape) and \
+            out.dtype == local.dtype and out.is_contiguous() and out.device.type == "cpu"
+        gathered = out if direct else torch.empty(gathered_dev.shape, dtype=local.dtype, pin_memory=True)
         gathered.copy_(gathered_dev, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         del gathered_dev
@@ -62,25 +72,34 @@ def sharded_map(fn: Callable[[torch.Tensor], torch.Tensor], rows: torch.Tensor, 
         slot[: hi - lo].copy_(local)
         gathered = torch.empty((world * width,) + shape, dtype=local.dtype)
         dist.all_gather_into_tensor(gathered, slot, group=group)
-    if width * world == n:
-        return gathered           # equal shards: the slots already are the rows in order
+    if width * world == n:        # equal shards: the slots already are the rows in order
+        if out is not None and gathered is not out:
+            out.copy_(gathered)
+            return out
+        return gathered
     parts = []
     for r in range(world):
         a, b = shard_bounds(n, r, world)
         parts.append(gathered[r * width: r * width + (b - a)])
+    if out is not None:
+        torch.cat(parts, dim=0, out=out)
+        return out
     return torch.cat(parts, dim=0)
 
 
 def generate_reflow_pairs_sharded(teacher_model, num_pairs: int, num_steps: int = 100,
                                   noise: Optional[torch.Tensor] = None, seed: int = 42, gather: bool = True,
-                                  group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                                  group=None, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Multi-GPU ``generate_reflow_pairs``: returns (x0, x1) as CPU fp32 tensors.  With gather=True both hold all
-    `num_pairs` rows on every rank; with gather=False they hold this rank's rows only."""
+    `num_pairs` rows on every rank; with gather=False they hold this rank's rows only.  `out` (optional): CPU tensor
+    [num_pairs, C, S, S] that receives the gathered x1 (see ``sharded_map``)."""
     teacher_model.eval()
     c, s = teacher_model.in_channels, teacher_model.image_size
     if noise is None:
         noise = seeded_noise(num_pairs, c, s, seed)
     noise = noise.to(torch.float32).cpu().contiguous()
+
+    on_device = gather and dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
 
     def integrate(x0: torch.Tensor) -> torch.Tensor:
         if x0.shape[0] == 0:
@@ -88,9 +107,12 @@ def generate_reflow_pairs_sharded(teacher_model, num_pairs: int, num_steps: int 
         x0 = x0.contiguous()
         if torch.cuda.is_available() and not x0.is_pinned():
             x0 = x0.pin_memory()
-        return teacher_model._engine(s).euler_sample_host(x0, num_steps)
+        eng = teacher_model._engine(s)
+        if on_device:   # the shard's result goes straight into the all-gather: it never visits the host on its own
+            return eng.euler_sample(x0.to(eng.device, non_blocking=True), num_steps)[0]
+        return eng.euler_sample_host(x0, num_steps)
 
-    x1 = sharded_map(integrate, noise, gather=gather, group=group)
+    x1 = sharded_map(integrate, noise, gather=gather, group=group, out=out)
     if gather or not (dist.is_available() and dist.is_initialized()):
         return noise, x1
     lo, hi = shard_bounds(num_pairs, dist.get_rank(group), dist.get_world_size(group))

@@ -37,7 +37,14 @@ def _worker(rank, world, port, n, out_dir):
     rows = rdist.seeded_noise(n, 3, 4, 7)
     full = rdist.sharded_map(_fake_integrate, rows, gather=True)
     part = rdist.sharded_map(_fake_integrate, rows, gather=False)
-    torch.save({"full": full, "part": part}, os.path.join(out_dir, f"r{rank}.pt"))
+    buf = torch.full_like(rows, -5.0)                     # caller-owned destination, re-used across two gathers
+    got = rdist.sharded_map(_fake_integrate, rows, gather=True, out=buf)
+    assert got is buf
+    rdist.sharded_map(_fake_integrate, rows, gather=True, out=buf)
+    even = rows[: (n // world) * world]                   # equal shards: the collective lands in `out` without a re-pack
+    buf2 = torch.empty_like(even)
+    assert rdist.sharded_map(_fake_integrate, even, gather=True, out=buf2) is buf2
+    torch.save({"full": full, "part": part, "out": buf, "out_even": buf2}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -53,11 +60,15 @@ def test_sharded_map_gloo_world2(tmp_path):
     r1 = torch.load(tmp_path / "r1.pt")
     assert torch.equal(r0["full"], want) and torch.equal(r1["full"], want)
     assert torch.equal(r0["part"], want[:4]) and torch.equal(r1["part"], want[4:])
+    assert torch.equal(r0["out"], want) and torch.equal(r1["out"], want)
+    assert torch.equal(r0["out_even"], want[:6]) and torch.equal(r1["out_even"], want[:6])
 
 
 def test_single_process_passthrough():
     rows = rdist.seeded_noise(3, 3, 4, 1)
     assert torch.equal(rdist.sharded_map(_fake_integrate, rows), _fake_integrate(rows))
+    buf = torch.empty_like(rows)
+    assert rdist.sharded_map(_fake_integrate, rows, out=buf) is buf and torch.equal(buf, _fake_integrate(rows))
 
 
 # ---- data-parallel training step: host-side sequence zero_grad -> accumulate -> all-reduce(SUM) -> step(1/world) ----

@@ -24,6 +24,18 @@ chk = torch.tensor([float(x1.double().sum())], device="cuda")
 all_chk = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(all_chk, chk)
 assert err < 2e-2, err
+buf = torch.empty(26, 3, 32, 32).pin_memory()            # caller-owned pinned destination, re-used across gathers
+for _ in range(2):
+    _, x1b = rdist.generate_reflow_pairs_sharded(m, num_pairs=26, num_steps=3, seed=42, gather=True, out=buf)
+    assert x1b is buf
+    eb = float(((x1b - ref) ** 2).sum().sqrt() / (ref ** 2).sum().sqrt())
+    rr = float(((x1b - x1) ** 2).sum().sqrt() / (x1 ** 2).sum().sqrt())   # run to run: summation order of the GroupNorm statistics
+    if rank == 0:
+        print(f"out= gather: rel-L2 vs single-rank {eb:.2e}, vs the first gather {rr:.2e}")
+    assert eb < 2e-2 and rr < 2e-2, (eb, rr)
+_, x1c = rdist.generate_reflow_pairs_sharded(m, num_pairs=25, num_steps=3, seed=42, gather=True, out=buf[:25])   # uneven shards
+ec = float(((x1c - ref[:25]) ** 2).sum().sqrt() / (ref[:25] ** 2).sum().sqrt())
+assert x1c.shape[0] == 25 and ec < 2e-2, ec
 assert all(abs(float(c) - float(all_chk[0])) < 1e-3 for c in all_chk), all_chk       # every rank holds the same gathered tensor
 # --- one data-parallel training step ---
 g = torch.Generator().manual_seed(100)
