@@ -10,7 +10,7 @@ No CPU fallback: the calls raise if the CUDA library is missing.
 from __future__ import annotations
 
 import time
-from typing import Dict, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch
@@ -24,6 +24,11 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def _sync():
+    if torch.cuda.is_available():   # (the timing loop itself is host logic; utils/metrics.py:150,158 guards the same way)
+        torch.cuda.synchronize()
 
 
 def fid_statistics(images: torch.Tensor, covariance: bool = True):
@@ -145,13 +150,35 @@ class MetricsCalculator:
             for run in range(num_runs):
                 if run == 0:
                     model.sample(torch.randn(1, 3, image_size, image_size).to(self.device), num_steps=num_steps)
-                torch.cuda.synchronize()
+                _sync()
                 t0 = time.time()
                 for i in range(0, num_samples, batch_size):
                     cur = min(batch_size, num_samples - i)
                     model.sample(torch.randn(cur, 3, image_size, image_size).to(self.device), num_steps=num_steps)
-                torch.cuda.synchronize()
+                _sync()
                 times.append(time.time() - t0)
         total = float(np.mean(times))
         return {"total_time": total, "time_per_image": total / num_samples, "images_per_second": num_samples / total,
                 "time_std": float(np.std(times)), "num_steps": num_steps, "num_samples": num_samples}
+
+
+def benchmark_models(base_model, rectified_model, steps_list: List[int], num_samples: int = 50, image_size: int = 64,
+                     device: str = "cuda") -> Dict:
+    """Generation speed of a base and a rectified model over a list of step counts (utils/metrics.py:175-222): same
+    arguments, same result dictionary ({'base_model': [...], 'rectified_model': [...]}, one speed record per step count
+    with 'model' added), same console report."""
+    calc = MetricsCalculator(device)
+    results = {"base_model": [], "rectified_model": []}
+    print("\n" + "=" * 60)
+    print("BENCHMARK: Modelo Base vs Modelo Rectificado")
+    print("=" * 60)
+    for num_steps in steps_list:
+        rec = {}
+        for key, tag, model in (("base_model", "base", base_model), ("rectified_model", "rectified", rectified_model)):
+            rec[tag] = calc.compute_generation_speed(model, num_samples, num_steps, image_size=image_size)
+            rec[tag]["model"] = tag
+            results[key].append(rec[tag])
+        print(f"\nPasos: {num_steps}")
+        print(f"  Base:       {rec['base']['time_per_image'] * 1000:.2f} ms/img")
+        print(f"  Rectified:  {rec['rectified']['time_per_image'] * 1000:.2f} ms/img")
+    return results

@@ -48,3 +48,33 @@ def test_nuclear_norm_form_equals_the_sqrtm_form(n1, n2, shape):
     ref, low = M.fid(x1, x2), M.fid_lowrank(x1, x2)
     assert abs(ref - low) <= 1e-6 * abs(ref), (ref, low)
     assert abs(M.fid_lowrank(x1, x1)) < 1e-9
+
+
+class _StubModel:
+    """Host-logic stand-in for a flow model: counts what the timing loops ask of it."""
+
+    def __init__(self):
+        self.calls = []
+
+    def eval(self):
+        return self
+
+    def sample(self, noise, num_steps=100):
+        self.calls.append((tuple(noise.shape), num_steps))
+        return noise
+
+
+def test_generation_speed_and_benchmark_models_host_logic(capsys):
+    """compute_generation_speed / benchmark_models (utils/metrics.py:118-222): batching, warm-up call, result keys."""
+    from rectified_flow_vision_b200.metrics import MetricsCalculator, benchmark_models
+    m = _StubModel()
+    r = MetricsCalculator(device="cpu").compute_generation_speed(m, num_samples=5, num_steps=3, batch_size=2, num_runs=2, image_size=8)
+    assert set(r) == {"total_time", "time_per_image", "images_per_second", "time_std", "num_steps", "num_samples"}
+    assert r["num_steps"] == 3 and r["num_samples"] == 5 and r["images_per_second"] > 0
+    # one warm-up sample of one image, then per run batches of 2, 2, 1
+    assert m.calls == [((1, 3, 8, 8), 3)] + [((2, 3, 8, 8), 3), ((2, 3, 8, 8), 3), ((1, 3, 8, 8), 3)] * 2
+    b, q = _StubModel(), _StubModel()
+    res = benchmark_models(b, q, steps_list=[1, 4], num_samples=2, image_size=8, device="cpu")
+    assert [x["num_steps"] for x in res["base_model"]] == [1, 4] and [x["model"] for x in res["rectified_model"]] == ["rectified"] * 2
+    out = capsys.readouterr().out
+    assert "BENCHMARK: Modelo Base vs Modelo Rectificado" in out and "Pasos: 4" in out
