@@ -4,6 +4,8 @@ Restates utils/metrics.py of the reference; that module cannot be imported here 
 skimage is not installed), so:
   * ``fid_statistics`` / ``fid`` are the reference's own numpy / scipy calls (utils/metrics.py:83-87 and :102-116) -- the
     arithmetic lives in numpy 2.3 / scipy 1.18 (installed), so these ARE the reference's results for the same inputs;
+    pinned by tests/golden/metrics.npz, which oracle/make_golden_metrics.py generates by running the reference's own
+    MetricsCalculator.compute_fid_statistics / compute_fid (file loaded unmodified, skimage import stubbed);
   * ``ssim`` restates skimage.metrics.structural_similarity (scikit-image==0.21.0, requirements.txt:10; scipy==1.11.3 is
     pinned at :8) as called at utils/metrics.py:52 -- ``channel_axis=2, data_range=255`` and otherwise defaults:
     win_size 7, uniform filter (scipy.ndimage.uniform_filter, which skimage itself calls), K1 = 0.01, K2 = 0.03,

@@ -9,6 +9,24 @@ from oracle import metrics_oracle as M
 pytestmark = pytest.mark.gpu
 
 
+def test_against_goldens_from_the_reference_calculator():
+    """tests/golden/metrics.npz (oracle/make_golden_metrics.py): statistics and FID from the reference's own
+    MetricsCalculator.compute_fid_statistics / compute_fid on seeded inputs; SSIM from the skimage restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz"))
+    c = _calc()
+    mu, sigma = c.compute_fid_statistics(torch.from_numpy(g["x_stats"]))
+    assert np.abs(mu - g["mu"]).max() <= 1e-6
+    assert np.abs(sigma - g["sigma"]).max() <= 2e-6 * np.abs(g["sigma"]).max()
+    for i, want in enumerate(g["fid"]):
+        got = c.compute_fid(torch.from_numpy(g[f"fid_a{i}"]), torch.from_numpy(g[f"fid_b{i}"]))
+        assert abs(got - want) <= 2e-6 * abs(want), (i, got, want)
+    same = c.compute_fid(torch.from_numpy(g["fid_a1"]), torch.from_numpy(g["fid_a1"]))
+    assert abs(same) < 1e-3 and abs(float(g["fid_identical"][0])) < 1e-3      # both ~0 (the reference's sqrtm: -3e-5)
+    for i, want in enumerate(g["ssim"]):
+        assert abs(c.compute_ssim(g[f"ssim_x{i}"], g[f"ssim_y{i}"]) - want) <= 1e-10
+
+
 def _calc():
     from rectified_flow_vision_b200.metrics import MetricsCalculator
     return MetricsCalculator(device="cuda:0")

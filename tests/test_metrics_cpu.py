@@ -3,7 +3,25 @@
 import numpy as np
 import pytest
 
+import os
+
 from oracle import metrics_oracle as M
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz")
+
+
+def test_oracle_reproduces_the_reference_goldens():
+    """tests/golden/metrics.npz: FID statistics / FID computed by the reference's OWN MetricsCalculator
+    (oracle/make_golden_metrics.py loads utils/metrics.py unmodified, skimage import stubbed, sqrtm `disp` shim)."""
+    g = np.load(GOLD)
+    mu, sigma = M.fid_statistics(g["x_stats"])
+    assert np.array_equal(mu.astype(np.float32), g["mu"]) and np.allclose(sigma, g["sigma"], rtol=1e-12, atol=1e-14)
+    for i, want in enumerate(g["fid"]):
+        got = M.fid(g[f"fid_a{i}"], g[f"fid_b{i}"])
+        assert abs(got - want) <= 1e-9 * abs(want), (i, got, want)
+        assert abs(M.fid_lowrank(g[f"fid_a{i}"], g[f"fid_b{i}"]) - want) <= 1e-6 * abs(want)
+    for i, want in enumerate(g["ssim"]):   # (these four come from the restatement itself: skimage is absent)
+        assert abs(M.ssim(g[f"ssim_x{i}"], g[f"ssim_y{i}"]) - want) <= 1e-14
 
 
 def test_ssim_reference_test_cases():
