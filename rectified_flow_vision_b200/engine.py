@@ -21,6 +21,7 @@ FLAG_ONE_LANE = 2
 FLAG_NO_GRAPH = 4194304
 FLAG_KEEP_ACTS = 4
 FLAG_TRAIN = 32
+FLAG_NO_PDL = 16777216   # RFV_FLAG_NO_PDL
 
 
 class RfvConfig(C.Structure):
@@ -163,6 +164,11 @@ class Engine:
             cfg.flags |= FLAG_ONE_LANE      # A/B: one chain of micro-batches instead of two alternately enqueued ones
         if train:
             cfg.flags |= FLAG_TRAIN
+        # Programmatic dependent launch pays on launch-bound micro-batches only; the library's bound is 128 images per call,
+        # calibrated at 64x64.  A kernel over 128 images of 128x128 is as long as one over 512 of 64x64, where dependent launch
+        # measured -1.2 %: scale the bound with the pixel count for larger images.
+        if image_size > 64 and cfg.micro_batch * image_size * image_size > 128 * 64 * 64:
+            cfg.flags |= FLAG_NO_PDL
         self.train = bool(cfg.flags & FLAG_TRAIN)
         self.micro_batch = cfg.micro_batch
         h = _VP()
